@@ -1,0 +1,138 @@
+/*
+ * kapre_b200 -- C ABI of the B200-native STFT -> |.| -> filterbank -> dB hot path (+ inverse STFT).
+ *
+ * This is the drop-in boundary of the repo: everything the reference computes inside
+ * TensorFlow for the five hot-path layers is reachable through these entry points, with
+ * plain pointers and sizes only (no torch / CUDA types in the signatures).  The Python
+ * layer classes in kapre_b200/ (mirrors of kapre.STFT / InverseSTFT / Magnitude /
+ * ApplyFilterbank / MagnitudeToDecibel) bind them with ctypes; INTEGRATION.md shows the
+ * stub a kapre maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative KAPRE_E_* code; the message is
+ *     available from kapre_last_error() (thread-local).  Nothing throws across the ABI.
+ *   - `*_dev` pointers are device pointers on the CUDA device that was current when the plan
+ *     was created; the caller owns every data buffer.  The library allocates only the small
+ *     constant tables held by plans (window, twiddles, banded filterbank).
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and returns; nothing synchronises.
+ *   - tensors are described by element strides, so both of kapre's data formats
+ *     ('channels_first' (B,C,T,F) / 'channels_last' (B,T,F,C); waveforms (B,C,L) / (B,L,C))
+ *     are served without transposes (replaces kapre/time_frequency.py:164-167,184-185,
+ *     304-305,316-317,546-547).
+ */
+#ifndef KAPRE_B200_H_
+#define KAPRE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAPRE_B200_VERSION 100
+
+enum {
+    KAPRE_OK = 0,
+    KAPRE_E_INVALID = -1,      /* bad argument */
+    KAPRE_E_UNSUPPORTED = -2,  /* valid in the reference but not implemented here */
+    KAPRE_E_CUDA = -3,         /* CUDA runtime error (see kapre_last_error) */
+    KAPRE_E_NOMEM = -4
+};
+
+/* What kapre_stft_forward writes.  One launch replaces the layer chain named on the right. */
+enum {
+    KAPRE_OUT_COMPLEX = 0, /* complex64   kapre.STFT                         time_frequency.py:146-187 */
+    KAPRE_OUT_MAG = 1,     /* float32     STFT -> Magnitude                  time_frequency.py:351-359 */
+    KAPRE_OUT_MAG_DB = 2,  /* float32     STFT -> Magnitude -> MagnitudeToDecibel      composed.py:32-135 */
+    KAPRE_OUT_FB = 3,      /* float32     STFT -> Magnitude -> ApplyFilterbank         composed.py:138-261 */
+    KAPRE_OUT_FB_DB = 4    /* float32     ... -> ApplyFilterbank -> MagnitudeToDecibel composed.py:254-261 */
+};
+
+/* Waveform tensor: element strides of (batch, channel, sample). */
+typedef struct {
+    int32_t batch, channels, length;
+    int64_t stride_b, stride_c, stride_l;
+} kapre_wave_desc;
+
+/* Spectrogram tensor: element strides of (batch, channel, frame, bin).  Elements are
+ * float32, or complex64 (one element = 8 bytes) for complex STFTs. */
+typedef struct {
+    int64_t stride_b, stride_c, stride_t, stride_f;
+} kapre_spec_desc;
+
+/* kapre.MagnitudeToDecibel(ref_value, amin, dynamic_range), kapre/backend.py:126-194. */
+typedef struct {
+    float ref_value, amin, dynamic_range;
+} kapre_db_cfg;
+
+typedef struct kapre_stft_plan kapre_stft_plan;
+typedef struct kapre_istft_plan kapre_istft_plan;
+typedef struct kapre_filterbank kapre_filterbank;
+
+/* ---- forward STFT (kapre.STFT.__init__/call, kapre/time_frequency.py:101-187) -------------
+ * `window_host`: win_length analysis-window samples (host memory), i.e. what
+ * backend.get_window_fn(window_name)(win_length) returns (kapre/backend.py:58-100).
+ * n_fft in {256,512,1024,2048} runs the fused FFT kernel; any other n_fft >= 2 runs the
+ * direct-DFT kernel (same results, slower). */
+int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const float* window_host,
+                           kapre_stft_plan** out);
+void kapre_stft_plan_destroy(kapre_stft_plan* plan);
+
+/* Frames produced for `length` samples: tf.signal.frame semantics after kapre's pad_begin
+ * (n_fft - hop zeros in front, kapre/time_frequency.py:169-172). */
+int kapre_stft_num_frames(const kapre_stft_plan* plan, int length, int pad_begin, int pad_end);
+
+/* 1 if kapre_stft_forward can produce `mode` in one fused launch for this plan. */
+int kapre_stft_supports_mode(const kapre_stft_plan* plan, int mode);
+
+/* Enqueue the transform.  `fb` is required for KAPRE_OUT_FB / _FB_DB, `db` for *_DB.
+ * `workspace_dev`: at least 4 * batch bytes, needed for *_DB (per-item maxima for the
+ * dynamic-range clamp of kapre/backend.py:190-192); may be NULL otherwise. */
+int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const kapre_wave_desc* x_desc,
+                       int pad_begin, int pad_end, int mode, void* out_dev,
+                       const kapre_spec_desc* out_desc, const kapre_filterbank* fb,
+                       const kapre_db_cfg* db, void* workspace_dev, void* stream);
+
+/* ---- inverse STFT (kapre.InverseSTFT, kapre/time_frequency.py:246-319) ---------------------
+ * `dual_window_host`: win_length samples of tf.signal.inverse_stft_window_fn(hop, forward
+ * window) (kapre/time_frequency.py:278-280).  Output length is (frames-1)*hop + win_length. */
+int kapre_istft_plan_create(int n_fft, int win_length, int hop_length, const float* dual_window_host,
+                            kapre_istft_plan** out);
+void kapre_istft_plan_destroy(kapre_istft_plan* plan);
+int kapre_istft_inverse(const kapre_istft_plan* plan, const void* stft_dev, int batch, int channels,
+                        int frames, const kapre_spec_desc* stft_desc, float* y_dev,
+                        const kapre_wave_desc* y_desc, void* stream);
+
+/* ---- filterbank (kapre.ApplyFilterbank, kapre/time_frequency.py:501-548) --------------------
+ * `fb_host`: row-major (n_freq, n_bands) float32 matrix, e.g. backend.filterbank_mel(...)
+ * (kapre/backend.py:197-231) or backend.filterbank_log(...) (kapre/backend.py:234-299). */
+int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre_filterbank** out);
+void kapre_filterbank_destroy(kapre_filterbank* fb);
+int kapre_apply_filterbank(const kapre_filterbank* fb, const float* x_dev, int batch, int channels,
+                           int frames, const kapre_spec_desc* x_desc, float* out_dev,
+                           const kapre_spec_desc* out_desc, void* stream);
+
+/* ---- element-wise layers ------------------------------------------------------------------- */
+/* kapre.Magnitude (tf.abs of complex64), kapre/time_frequency.py:351-359; n complex elements. */
+int kapre_magnitude(const void* x_complex_dev, float* out_dev, int64_t n, void* stream);
+/* kapre.Phase (tf.math.angle), kapre/time_frequency.py:391-402; n complex elements. */
+int kapre_phase(const void* x_complex_dev, float* out_dev, int64_t n, void* stream);
+/* backend.magnitude_to_decibel on a contiguous (n_items, item_size) tensor: the maximum for the
+ * dynamic-range clamp is taken per item (kapre/backend.py:178-192); pass n_items = 1 for a
+ * 1-D input (global maximum).  workspace_dev: >= 4 * n_items bytes.  In-place is allowed. */
+int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_items, int64_t item_size,
+                               const kapre_db_cfg* db, void* workspace_dev, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+const char* kapre_last_error(void);
+int kapre_version(void);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+uint64_t kapre_launch_count(void);
+/* Name of the last fused-forward launch configuration, e.g. "Q16 TF16 NW4 grid296 smem98304". */
+const char* kapre_last_launch_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAPRE_B200_H_ */

@@ -1,0 +1,188 @@
+"""Mirrors of the hot-path factories of ``kapre/composed.py`` plus the ``Sequential`` container.
+
+``get_melspectrogram_layer`` (reference kapre/composed.py:138-261), ``get_stft_magnitude_layer``
+(:32-135) and ``get_perfectly_reconstructing_stft_istft`` (:388-417) keep their signatures and
+return the same layer stacks.  ``Sequential`` recognises the stack
+``[STFT, Magnitude, (ApplyFilterbank), (MagnitudeToDecibel)]`` and runs it as ONE fused CUDA
+launch (magnitudes never reach HBM); ``.layers`` remains usable one by one
+(kapre/composed.py:5-12) and gives the same results through the stand-alone kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import backend, ops
+from .backend import _CH_DEFAULT_STR, _CH_FIRST_STR, _CH_LAST_STR
+from .time_frequency import (STFT, ApplyFilterbank, InverseSTFT, Layer, Magnitude, MagnitudeToDecibel, Phase,
+                             get_registered_object)
+
+__all__ = ['Sequential', 'get_stft_magnitude_layer', 'get_melspectrogram_layer',
+           'get_log_frequency_spectrogram_layer', 'get_perfectly_reconstructing_stft_istft']
+
+
+class Sequential(Layer):
+    """Minimal ``keras.Sequential``: ``add``, ``layers``, ``__call__``, ``predict``, config."""
+
+    def __init__(self, layers=None, name=None, fuse=True):
+        super().__init__(name=name)
+        self.layers = []
+        self.fuse = fuse
+        for layer in (layers or []):
+            self.add(layer)
+
+    def add(self, layer):
+        if not isinstance(layer, Layer):
+            raise TypeError('Sequential only takes kapre_b200 layers, got %r' % (layer,))
+        self.layers.append(layer)
+
+    # -- fusion -----------------------------------------------------------------------------
+    def _fused_prefix(self):
+        """(n_layers_consumed, mode, stft, filterbank_layer, db_layer) for the longest leading
+        run that one fused launch covers, or None."""
+        ls = self.layers
+        if not self.fuse or len(ls) < 2 or type(ls[0]) is not STFT or type(ls[1]) is not Magnitude:
+            return None
+        stft = ls[0]
+        n, mode, fbl, dbl = 2, N.OUT_MAG, None, None
+        if len(ls) > n and type(ls[n]) is ApplyFilterbank and hasattr(ls[n], 'filterbank') \
+                and ls[n].data_format == stft.output_data_format \
+                and ls[n].filterbank.shape[0] == stft.n_fft // 2 + 1:
+            fbl, mode, n = ls[n], N.OUT_FB, n + 1
+        if len(ls) > n and type(ls[n]) is MagnitudeToDecibel:
+            dbl, n = ls[n], n + 1
+            mode = N.OUT_FB_DB if fbl is not None else N.OUT_MAG_DB
+        if not stft.plan.supports_mode(mode):
+            return None
+        return n, mode, stft, fbl, dbl
+
+    def call(self, x):
+        start = 0
+        fused = self._fused_prefix() if (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 3) else None
+        if fused is not None:
+            n, mode, stft, fbl, dbl = fused
+            db = None
+            if dbl is not None:
+                # same call-time validation as backend.magnitude_to_decibel (kapre/backend.py:168-173)
+                if dbl.ref_value <= 0:
+                    raise ValueError('ref_value must be positive, got: %s' % (dbl.ref_value,))
+                if dbl.amin <= 0:
+                    raise ValueError('amin must be positive, got: %s' % (dbl.amin,))
+                if dbl.dynamic_range <= 0:
+                    raise ValueError('dynamic_range must be positive, got: %s' % (dbl.dynamic_range,))
+                db = (dbl.ref_value, dbl.amin, dbl.dynamic_range)
+            x = ops.stft_forward(x, stft.plan, stft.input_data_format, stft.output_data_format, stft.pad_begin,
+                                 stft.pad_end, mode, fbl.fb if fbl is not None else None, db)
+            start = n
+        for layer in self.layers[start:]:
+            x = layer.call(x)
+        return x
+
+    def predict(self, x, batch_size=None, verbose=0, **kwargs):
+        """Like ``keras.Model.predict``: host array in, host array out.  ``batch_size`` only bounds
+        how many items are resident on the device at once (results do not depend on it: every op
+        on the path, including the decibel clamp, is per batch item)."""
+        if batch_size is None or batch_size <= 0 or len(x) <= batch_size:
+            y = self(x)
+            return ops.to_host(y) if isinstance(y, torch.Tensor) else y
+        outs = [self.predict(x[i:i + batch_size]) for i in range(0, len(x), batch_size)]
+        return np.concatenate(outs, axis=0)
+
+    # -- serialisation ------------------------------------------------------------------------
+    def get_config(self):
+        return {'name': self.name,
+                'layers': [{'class_name': type(l).__name__,
+                            'registered_name': getattr(type(l), '_registered_name', None),
+                            'config': l.get_config()} for l in self.layers]}
+
+    @classmethod
+    def from_config(cls, config):
+        layers = []
+        for item in config['layers']:
+            klass = get_registered_object(item.get('registered_name')) or globals().get(item['class_name'])
+            if klass is None:
+                raise ValueError('Unknown layer class %r' % (item['class_name'],))
+            layers.append(klass.from_config(dict(item['config'])))
+        return cls(layers, name=config.get('name'))
+
+
+def get_stft_magnitude_layer(input_shape=None, n_fft=2048, win_length=None, hop_length=None, window_name=None,
+                             pad_begin=False, pad_end=False, return_decibel=False, db_amin=1e-5,
+                             db_ref_value=1.0, db_dynamic_range=80.0, input_data_format='default',
+                             output_data_format='default', name='stft_magnitude'):
+    """``Sequential([STFT, Magnitude, (MagnitudeToDecibel)])`` -- kapre/composed.py:32-135."""
+    backend.validate_data_format_str(input_data_format)
+    backend.validate_data_format_str(output_data_format)
+    stft_kwargs = {}
+    if input_shape is not None:
+        stft_kwargs['input_shape'] = input_shape
+    waveform_to_stft = STFT(**stft_kwargs, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+                            window_name=window_name, pad_begin=pad_begin, pad_end=pad_end,
+                            input_data_format=input_data_format, output_data_format=output_data_format)
+    layers = [waveform_to_stft, Magnitude()]
+    if return_decibel:
+        layers.append(MagnitudeToDecibel(ref_value=db_ref_value, amin=db_amin, dynamic_range=db_dynamic_range))
+    return Sequential(layers, name=name)
+
+
+def get_melspectrogram_layer(input_shape=None, n_fft=2048, win_length=None, hop_length=None, window_name=None,
+                             pad_begin=False, pad_end=False, sample_rate=22050, n_mels=128, mel_f_min=0.0,
+                             mel_f_max=None, mel_htk=False, mel_norm='slaney', return_decibel=False,
+                             db_amin=1e-5, db_ref_value=1.0, db_dynamic_range=80.0, input_data_format='default',
+                             output_data_format='default', name='melspectrogram'):
+    """``Sequential([STFT, Magnitude, ApplyFilterbank('mel'), (MagnitudeToDecibel)])`` --
+    kapre/composed.py:138-261.  Called on a CUDA tensor the whole stack is one fused kernel."""
+    backend.validate_data_format_str(input_data_format)
+    backend.validate_data_format_str(output_data_format)
+    stft_kwargs = {}
+    if input_shape is not None:
+        stft_kwargs['input_shape'] = input_shape
+    waveform_to_stft = STFT(**stft_kwargs, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+                            window_name=window_name, pad_begin=pad_begin, pad_end=pad_end,
+                            input_data_format=input_data_format, output_data_format=output_data_format)
+    kwargs = {'sample_rate': sample_rate, 'n_freq': n_fft // 2 + 1, 'n_mels': n_mels, 'f_min': mel_f_min,
+              'f_max': mel_f_max, 'htk': mel_htk, 'norm': mel_norm}
+    stftm_to_melgram = ApplyFilterbank(type='mel', filterbank_kwargs=kwargs, data_format=output_data_format)
+    layers = [waveform_to_stft, Magnitude(), stftm_to_melgram]
+    if return_decibel:
+        layers.append(MagnitudeToDecibel(ref_value=db_ref_value, amin=db_amin, dynamic_range=db_dynamic_range))
+    return Sequential(layers, name=name)
+
+
+def get_log_frequency_spectrogram_layer(input_shape=None, n_fft=2048, win_length=None, hop_length=None,
+                                        window_name=None, pad_begin=False, pad_end=False, sample_rate=22050,
+                                        log_n_bins=84, log_f_min=None, log_bins_per_octave=12, log_spread=0.125,
+                                        return_decibel=False, db_amin=1e-5, db_ref_value=1.0,
+                                        db_dynamic_range=80.0, input_data_format='default',
+                                        output_data_format='default', name='log_frequency_spectrogram'):
+    """Same stack with the log-frequency filterbank -- kapre/composed.py:264-385."""
+    backend.validate_data_format_str(input_data_format)
+    backend.validate_data_format_str(output_data_format)
+    stft_kwargs = {}
+    if input_shape is not None:
+        stft_kwargs['input_shape'] = input_shape
+    waveform_to_stft = STFT(**stft_kwargs, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+                            window_name=window_name, pad_begin=pad_begin, pad_end=pad_end,
+                            input_data_format=input_data_format, output_data_format=output_data_format)
+    kwargs = {'sample_rate': sample_rate, 'n_freq': n_fft // 2 + 1, 'n_bins': log_n_bins,
+              'bins_per_octave': log_bins_per_octave, 'f_min': log_f_min, 'spread': log_spread}
+    stftm_to_loggram = ApplyFilterbank(type='log', filterbank_kwargs=kwargs, data_format=output_data_format)
+    layers = [waveform_to_stft, Magnitude(), stftm_to_loggram]
+    if return_decibel:
+        layers.append(MagnitudeToDecibel(ref_value=db_ref_value, amin=db_amin, dynamic_range=db_dynamic_range))
+    return Sequential(layers, name=name)
+
+
+def get_perfectly_reconstructing_stft_istft(n_fft, hop_length, waveform_data_format, stft_data_format,
+                                            stft_name=None, istft_name=None):
+    """The (STFT, InverseSTFT) pair of kapre/composed.py:388-417: Hann window of ``n_fft`` samples,
+    ``pad_begin`` and ``pad_end`` on, so that STFT -> InverseSTFT reproduces the waveform after
+    trimming the first ``n_fft - hop_length`` samples."""
+    stft = STFT(n_fft=n_fft, win_length=n_fft, hop_length=hop_length, window_name='hann_window', pad_begin=True,
+                pad_end=True, input_data_format=waveform_data_format, output_data_format=stft_data_format,
+                name=stft_name)
+    istft = InverseSTFT(n_fft=n_fft, win_length=n_fft, hop_length=hop_length, forward_window_name='hann_window',
+                        input_data_format=stft_data_format, output_data_format=waveform_data_format,
+                        name=istft_name)
+    return stft, istft

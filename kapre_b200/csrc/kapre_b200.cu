@@ -1,0 +1,671 @@
+// kapre_b200 -- CUDA kernels (sm_100a) and the C ABI declared in include/kapre_b200.h.
+//
+// Kernel bodies live in stft_core.cuh / istft_core.cuh / aux_core.cuh (shared with the CPU
+// emulation harness under tests/emu); this file holds the __global__ wrappers, the
+// element-wise kernels, launch-configuration logic and the extern "C" entry points.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/kapre_b200.h"
+#include "kb_tables.h"
+#include "stft_core.cuh"
+#include "istft_core.cuh"
+#include "aux_core.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local std::string g_launch_info;
+static std::atomic<uint64_t> g_launches{0};
+
+static int kb_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define KB_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return kb_fail(KAPRE_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                           __FILE__, __LINE__);                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// __global__ wrappers
+// ------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_stft_kernel(const __grid_constant__ KbStftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_stft_cta<Q>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+template <int Q>
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_istft_kernel(const __grid_constant__ KbIstftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_istft_cta<Q>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_fb_kernel(const __grid_constant__ KbFbParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_fb_cta(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_dft_kernel(const __grid_constant__ KbDftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_dft_cta(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_idft_kernel(const __grid_constant__ KbIdftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_idft_cta(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Dynamic-range clamp, kapre/backend.py:190-192: y = max(y, max_item(y) - dynamic_range).
+// item_max holds max(x, amin) per item (uint view); log is monotone, so the item maximum in
+// dB is dB(item_max).  Exits immediately when the clamp cannot bind (threshold <= dB(amin)),
+// which is the common case, so no output byte is re-read.
+__global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size, int chunks,
+                                   const unsigned int* __restrict__ item_max, float amin,
+                                   float db_mul, float db_sub, float dyn_range) {
+    const long long item = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - (int)(item * chunks);
+    const float mx = __uint_as_float(item_max[item]);
+    const float thr = (db_mul * __log2f(fmaxf(mx, amin)) - db_sub) - dyn_range;
+    const float floor_db = db_mul * __log2f(amin) - db_sub;
+    if (!(thr > floor_db)) return;
+    float* yi = y + item * item_size;
+    for (long long i = (long long)chunk * blockDim.x + threadIdx.x; i < item_size;
+         i += (long long)chunks * blockDim.x)
+        yi[i] = fmaxf(yi[i], thr);
+}
+
+// Stand-alone MagnitudeToDecibel pass 1: y = db(max(x, amin)), per-item max of max(x, amin).
+__global__ void kb_db_kernel(const float* __restrict__ x, float* __restrict__ y, long long item_size,
+                             int chunks, unsigned int* __restrict__ item_max, float amin,
+                             float db_mul, float db_sub) {
+    const long long item = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - (int)(item * chunks);
+    const float* xi = x + item * item_size;
+    float* yi = y + item * item_size;
+    float mx = 0.0f;
+    for (long long i = (long long)chunk * blockDim.x + threadIdx.x; i < item_size;
+         i += (long long)chunks * blockDim.x) {
+        const float v = fmaxf(xi[i], amin);
+        mx = fmaxf(mx, v);
+        yi[i] = db_mul * __log2f(v) - db_sub;
+    }
+    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    if ((threadIdx.x & 31) == 0 && wm != 0u) atomicMax(item_max + item, wm);
+}
+
+__global__ void kb_magnitude_kernel(const float2* __restrict__ x, float* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = x[i];
+        y[i] = kb_sqrt(v.x * v.x + v.y * v.y);
+    }
+}
+
+__global__ void kb_phase_kernel(const float2* __restrict__ x, float* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = x[i];
+        y[i] = atan2f(v.y, v.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------
+struct DevInfo {
+    int device = -1;
+    int sm_count = 0;
+    int smem_optin = 0;
+};
+
+static int kb_dev_info(DevInfo* d) {
+    KB_CUDA(cudaGetDevice(&d->device));
+    KB_CUDA(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, d->device));
+    KB_CUDA(cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
+    return 0;
+}
+
+template <typename T>
+static int kb_upload(const std::vector<T>& h, T** d) {
+    KB_CUDA(cudaMalloc((void**)d, h.size() * sizeof(T)));
+    KB_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+struct kapre_stft_plan {
+    int n_fft, win_length, hop, Q;
+    DevInfo dev;
+    float* wh = nullptr;      // fused path: 0.5 * window padded to n_fft
+    float2* twp = nullptr;
+    float2* twn = nullptr;
+    float* w = nullptr;       // generic path: window[0, win_eff)
+    float2* tw = nullptr;     // generic path: exp(-2 pi i r / n_fft)
+    int win_eff;
+};
+
+struct kapre_istft_plan {
+    int n_fft, win_length, hop, Q, win;
+    DevInfo dev;
+    float* dual = nullptr;    // fused path (kb_make_dual)
+    float2* twp = nullptr;
+    float2* twn = nullptr;
+    float* dualn = nullptr;   // generic path: dual / n_fft
+    float2* tw = nullptr;     // generic path: exp(+2 pi i r / n_fft)
+};
+
+struct kapre_filterbank {
+    int n_freq, n_bands;
+    DevInfo dev;
+    KbBand* bands = nullptr;
+    float* w = nullptr;
+};
+
+static int kb_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch configuration of the fused forward kernel
+// ------------------------------------------------------------------------------------------
+struct FwdCfg { int TF, NW, smem, bps; };
+
+static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int mode, int n_bands, FwdCfg* out) {
+    const int FPW = 32 / Q;
+    const int force_tf = kb_env_int("KAPRE_B200_TF", 0);
+    const int force_nw = kb_env_int("KAPRE_B200_NW", 0);
+    const int sm_smem = 228 * 1024;
+    bool found = false;
+    FwdCfg best{};
+    long best_score = -1;
+    const int nws[2] = {4, 8};
+    for (int a = 0; a < 2; ++a) {
+        const int NW = nws[a];
+        if (force_nw && NW != force_nw) continue;
+        for (int TF = 32; TF >= 1; TF >>= 1) {
+            if (force_tf && TF != force_tf) continue;
+            if (TF % FPW) continue;
+            if (!force_tf && TF < NW * FPW) continue;   // would leave warps without a frame
+            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands);
+            if (L.total > dev.smem_optin) continue;
+            int bps = sm_smem / (L.total + 1024);
+            if (bps > 64 / NW) bps = 64 / NW;
+            if (bps > 32) bps = 32;
+            if (bps < 1) continue;
+            int warps = bps * NW;
+            if (warps > 16) warps = 16;
+            const long score = (long)warps * 1000 + TF * 10 + (NW == 4 ? 1 : 0);
+            if (score > best_score) {
+                best_score = score;
+                best = FwdCfg{TF, NW, L.total, bps};
+                found = true;
+            }
+        }
+    }
+    *out = best;
+    return found;
+}
+
+template <typename K>
+static int kb_set_smem(K kernel, int smem) {
+    if (smem > 48 * 1024)
+        KB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return 0;
+}
+
+template <int Q>
+static int kb_launch_stft(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    int rc = kb_set_smem(kb_stft_kernel<Q>, smem);
+    if (rc) return rc;
+    kb_stft_kernel<Q><<<grid, p.n_warps * 32, smem, st>>>(p);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+template <int Q>
+static int kb_launch_istft(const KbIstftParams& p, int grid, int smem, cudaStream_t st) {
+    int rc = kb_set_smem(kb_istft_kernel<Q>, smem);
+    if (rc) return rc;
+    kb_istft_kernel<Q><<<grid, p.n_warps * 32, smem, st>>>(p);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+static int kb_check_device(const DevInfo& d) {
+    int cur = -1;
+    KB_CUDA(cudaGetDevice(&cur));
+    if (cur != d.device)
+        return kb_fail(KAPRE_E_INVALID, "plan was created on device %d but device %d is current", d.device, cur);
+    return 0;
+}
+
+static int kb_launch_clamp(float* y, long long n_items, long long item_size, const unsigned int* item_max,
+                           float amin, float db_mul, float db_sub, float dr, cudaStream_t st) {
+    if (n_items <= 0 || item_size <= 0) return 0;
+    long long chunks = (item_size + 256 * 8 - 1) / (256 * 8);
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    const long long grid = n_items * chunks;
+    if (grid > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items for the clamp kernel");
+    kb_db_clamp_kernel<<<(unsigned)grid, 256, 0, st>>>(y, item_size, (int)chunks, item_max, amin, db_mul, db_sub, dr);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+static void kb_db_consts(const kapre_db_cfg* db, float* db_mul, float* db_sub) {
+    // 10*log10(v) = (10*log10(2)) * log2(v);  kapre/backend.py:187-188
+    *db_mul = (float)(10.0 * log10(2.0));
+    const double m = db->amin > db->ref_value ? db->amin : db->ref_value;
+    *db_sub = (float)(10.0 * log10(m));
+}
+
+static int kb_check_db(const kapre_db_cfg* db) {
+    if (!db) return kb_fail(KAPRE_E_INVALID, "decibel configuration required");
+    // kapre/backend.py:168-173
+    if (!(db->ref_value > 0)) return kb_fail(KAPRE_E_INVALID, "ref_value must be positive, got: %g", db->ref_value);
+    if (!(db->amin > 0)) return kb_fail(KAPRE_E_INVALID, "amin must be positive, got: %g", db->amin);
+    if (!(db->dynamic_range > 0)) return kb_fail(KAPRE_E_INVALID, "dynamic_range must be positive, got: %g", db->dynamic_range);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* kapre_last_error(void) { return g_err.c_str(); }
+int kapre_version(void) { return KAPRE_B200_VERSION; }
+uint64_t kapre_launch_count(void) { return g_launches.load(); }
+const char* kapre_last_launch_info(void) { return g_launch_info.c_str(); }
+
+int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const float* window_host,
+                           kapre_stft_plan** out) {
+    if (!out || !window_host) return kb_fail(KAPRE_E_INVALID, "null argument");
+    if (n_fft < 2 || win_length < 1 || hop_length < 1)
+        return kb_fail(KAPRE_E_INVALID, "n_fft=%d win_length=%d hop_length=%d out of range", n_fft, win_length, hop_length);
+    if (n_fft > 16384) return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d > 16384 is not supported", n_fft);
+    kapre_stft_plan* p = new kapre_stft_plan();
+    p->n_fft = n_fft; p->win_length = win_length; p->hop = hop_length;
+    p->Q = kb_q_for_nfft(n_fft);
+    p->win_eff = win_length < n_fft ? win_length : n_fft;
+    int rc = kb_dev_info(&p->dev);
+    if (rc) { delete p; return rc; }
+    if (p->Q) {
+        std::vector<float> wh; std::vector<float2> twp, twn;
+        kb_make_wh(window_host, win_length, n_fft, wh);
+        kb_make_twp(p->Q, twp);
+        kb_make_twn(n_fft, twn);
+        if ((rc = kb_upload(wh, &p->wh)) || (rc = kb_upload(twp, &p->twp)) || (rc = kb_upload(twn, &p->twn))) {
+            kapre_stft_plan_destroy(p); return rc;
+        }
+    }
+    {   // generic tables are always built: they also serve sizes the fused kernel cannot take
+        std::vector<float> w(window_host, window_host + p->win_eff);
+        std::vector<float2> tw(n_fft);
+        for (int r = 0; r < n_fft; ++r) {
+            const double a = -2.0 * M_PI * (double)r / (double)n_fft;
+            tw[r] = make_float2((float)cos(a), (float)sin(a));
+        }
+        if ((rc = kb_upload(w, &p->w)) || (rc = kb_upload(tw, &p->tw))) { kapre_stft_plan_destroy(p); return rc; }
+    }
+    *out = p;
+    return 0;
+}
+
+void kapre_stft_plan_destroy(kapre_stft_plan* p) {
+    if (!p) return;
+    cudaFree(p->wh); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->w); cudaFree(p->tw);
+    delete p;
+}
+
+int kapre_stft_num_frames(const kapre_stft_plan* p, int length, int pad_begin, int pad_end) {
+    if (!p || length < 0) return kb_fail(KAPRE_E_INVALID, "bad argument");
+    const long long Lp = (long long)length + (pad_begin ? (p->n_fft - p->hop) : 0);
+    if (pad_end) return (int)((Lp + p->hop - 1) / p->hop);
+    if (Lp < p->win_length) return 0;
+    return (int)(1 + (Lp - p->win_length) / p->hop);
+}
+
+int kapre_stft_supports_mode(const kapre_stft_plan* p, int mode) {
+    if (!p) return 0;
+    if (mode < KAPRE_OUT_COMPLEX || mode > KAPRE_OUT_FB_DB) return 0;
+    if (p->Q) return 1;
+    return mode == KAPRE_OUT_COMPLEX || mode == KAPRE_OUT_MAG;
+}
+
+int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const kapre_wave_desc* xd,
+                       int pad_begin, int pad_end, int mode, void* out_dev, const kapre_spec_desc* od,
+                       const kapre_filterbank* fb, const kapre_db_cfg* db, void* workspace_dev, void* stream) {
+    if (!plan || !xd || !od) return kb_fail(KAPRE_E_INVALID, "null argument");
+    if (mode < KAPRE_OUT_COMPLEX || mode > KAPRE_OUT_FB_DB) return kb_fail(KAPRE_E_INVALID, "bad mode %d", mode);
+    int rc = kb_check_device(plan->dev);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = xd->batch, C = xd->channels, Ln = xd->length;
+    if (B < 0 || C < 0 || Ln < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    const int T = kapre_stft_num_frames(plan, Ln, pad_begin, pad_end);
+    if (B == 0 || C == 0 || T <= 0) return 0;
+    if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    if ((long long)T * plan->hop + plan->n_fft > 0x7fffffffLL)
+        return kb_fail(KAPRE_E_UNSUPPORTED, "signal too long");
+    const bool fbmode = (mode == KAPRE_OUT_FB || mode == KAPRE_OUT_FB_DB);
+    const bool dbmode = (mode == KAPRE_OUT_MAG_DB || mode == KAPRE_OUT_FB_DB);
+    if (fbmode) {
+        if (!fb) return kb_fail(KAPRE_E_INVALID, "filterbank required for mode %d", mode);
+        if (fb->n_freq != plan->n_fft / 2 + 1)
+            return kb_fail(KAPRE_E_INVALID, "filterbank has %d rows but n_fft/2+1 = %d", fb->n_freq, plan->n_fft / 2 + 1);
+        if (fb->dev.device != plan->dev.device) return kb_fail(KAPRE_E_INVALID, "filterbank lives on another device");
+    }
+    float db_mul = 0, db_sub = 0;
+    if (dbmode) {
+        if ((rc = kb_check_db(db))) return rc;
+        if (!workspace_dev) return kb_fail(KAPRE_E_INVALID, "workspace required for decibel modes");
+        kb_db_consts(db, &db_mul, &db_sub);
+    }
+    const int pad_left = pad_begin ? (plan->n_fft - plan->hop) : 0;
+
+    if (!plan->Q) {
+        if (!(mode == KAPRE_OUT_COMPLEX || mode == KAPRE_OUT_MAG))
+            return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d has no fused filterbank/decibel path; chain the stand-alone ops", plan->n_fft);
+        KbDftParams p{};
+        p.x = x_dev; p.x_sb = xd->stride_b; p.x_sc = xd->stride_c; p.x_sl = xd->stride_l;
+        p.B = B; p.C = C; p.L = Ln; p.n_fft = plan->n_fft; p.hop = plan->hop; p.T = T; p.pad_left = pad_left;
+        p.win_eff = plan->win_eff; p.w = plan->w; p.tw = plan->tw;
+        p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
+        p.mode = mode; p.n_tiles_t = (T + KB_DFT_TF - 1) / KB_DFT_TF; p.n_warps = 8;
+        const KbDftSmem L = kb_dft_smem_layout(plan->n_fft, plan->win_eff);
+        if (L.total > plan->dev.smem_optin) return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d too large for the direct-DFT kernel", plan->n_fft);
+        if ((rc = kb_set_smem(kb_dft_kernel, L.total))) return rc;
+        long long tiles = (long long)B * C * p.n_tiles_t;
+        int grid = (int)(tiles < plan->dev.sm_count * 4LL ? tiles : plan->dev.sm_count * 4LL);
+        kb_dft_kernel<<<grid, 256, L.total, st>>>(p);
+        KB_CUDA(cudaGetLastError());
+        g_launches++;
+        return 0;
+    }
+
+    FwdCfg cfg;
+    if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0, &cfg))
+        return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
+                       plan->n_fft, plan->hop, fbmode ? fb->n_bands : 0);
+    KbStftParams p{};
+    p.x = x_dev; p.x_sb = xd->stride_b; p.x_sc = xd->stride_c; p.x_sl = xd->stride_l;
+    p.B = B; p.C = C; p.L = Ln; p.n_fft = plan->n_fft; p.hop = plan->hop; p.T = T; p.pad_left = pad_left;
+    p.wh = plan->wh; p.twp = plan->twp; p.twn = plan->twn;
+    p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
+    p.mode = mode;
+    if (fbmode) { p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands; }
+    if (dbmode) { p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev; }
+    p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
+    const long long tiles = (long long)B * C * p.n_tiles_t;
+    if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
+    long long gmax = (long long)plan->dev.sm_count * cfg.bps;
+    const int grid = (int)(tiles < gmax ? tiles : gmax);
+    if (dbmode) KB_CUDA(cudaMemsetAsync(workspace_dev, 0, (size_t)B * 4, st));
+    switch (plan->Q) {
+        case 4: rc = kb_launch_stft<4>(p, grid, cfg.smem, st); break;
+        case 8: rc = kb_launch_stft<8>(p, grid, cfg.smem, st); break;
+        case 16: rc = kb_launch_stft<16>(p, grid, cfg.smem, st); break;
+        case 32: rc = kb_launch_stft<32>(p, grid, cfg.smem, st); break;
+        default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+    }
+    if (rc) return rc;
+    {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "Q%d TF%d NW%d grid%d smem%d bps%d tiles%lld", plan->Q, cfg.TF, cfg.NW, grid, cfg.smem, cfg.bps, tiles);
+        g_launch_info = buf;
+    }
+    if (dbmode) {
+        // items are contiguous blocks of stride_b elements in both data formats
+        const long long K = fbmode ? fb->n_bands : (plan->n_fft / 2 + 1);
+        const long long item_size = (long long)C * T * K;
+        if (od->stride_b != item_size)
+            return kb_fail(KAPRE_E_UNSUPPORTED, "decibel modes need a batch-contiguous output (stride_b=%lld, item=%lld)",
+                           (long long)od->stride_b, item_size);
+        rc = kb_launch_clamp((float*)out_dev, B, item_size, (const unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
+                             db->dynamic_range, st);
+    }
+    return rc;
+}
+
+int kapre_istft_plan_create(int n_fft, int win_length, int hop_length, const float* dual_window_host,
+                            kapre_istft_plan** out) {
+    if (!out || !dual_window_host) return kb_fail(KAPRE_E_INVALID, "null argument");
+    if (n_fft < 2 || win_length < 1 || hop_length < 1)
+        return kb_fail(KAPRE_E_INVALID, "n_fft=%d win_length=%d hop_length=%d out of range", n_fft, win_length, hop_length);
+    if (n_fft > 16384) return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d > 16384 is not supported", n_fft);
+    kapre_istft_plan* p = new kapre_istft_plan();
+    p->n_fft = n_fft; p->win_length = win_length; p->hop = hop_length;
+    p->Q = kb_q_for_nfft(n_fft);
+    p->win = win_length < n_fft ? win_length : n_fft;
+    int rc = kb_dev_info(&p->dev);
+    if (rc) { delete p; return rc; }
+    if (p->Q) {
+        std::vector<float> dual; std::vector<float2> twp, twn;
+        kb_make_dual(dual_window_host, p->win, n_fft, dual);
+        kb_make_twp(p->Q, twp);
+        kb_make_twn(n_fft, twn);
+        if ((rc = kb_upload(dual, &p->dual)) || (rc = kb_upload(twp, &p->twp)) || (rc = kb_upload(twn, &p->twn))) {
+            kapre_istft_plan_destroy(p); return rc;
+        }
+    }
+    {
+        std::vector<float> dn(p->win);
+        for (int m = 0; m < p->win; ++m) dn[m] = (float)((double)dual_window_host[m] / (double)n_fft);
+        std::vector<float2> tw(n_fft);
+        for (int r = 0; r < n_fft; ++r) {
+            const double a = 2.0 * M_PI * (double)r / (double)n_fft;
+            tw[r] = make_float2((float)cos(a), (float)sin(a));
+        }
+        if ((rc = kb_upload(dn, &p->dualn)) || (rc = kb_upload(tw, &p->tw))) { kapre_istft_plan_destroy(p); return rc; }
+    }
+    *out = p;
+    return 0;
+}
+
+void kapre_istft_plan_destroy(kapre_istft_plan* p) {
+    if (!p) return;
+    cudaFree(p->dual); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->dualn); cudaFree(p->tw);
+    delete p;
+}
+
+int kapre_istft_inverse(const kapre_istft_plan* plan, const void* stft_dev, int batch, int channels, int frames,
+                        const kapre_spec_desc* sd, float* y_dev, const kapre_wave_desc* yd, void* stream) {
+    if (!plan || !sd || !yd) return kb_fail(KAPRE_E_INVALID, "null argument");
+    int rc = kb_check_device(plan->dev);
+    if (rc) return rc;
+    if (batch < 0 || channels < 0 || frames < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    if (batch == 0 || channels == 0 || frames == 0) return 0;
+    if (!stft_dev || !y_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long out_len = (long long)(frames - 1) * plan->hop + plan->win_length;
+    if (out_len > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "signal too long");
+    if (yd->length != (int)out_len)
+        return kb_fail(KAPRE_E_INVALID, "output length must be (frames-1)*hop+win_length = %lld, got %d", out_len, yd->length);
+
+    if (!plan->Q) {
+        KbIdftParams p{};
+        p.X = (const float2*)stft_dev; p.x_sb = sd->stride_b; p.x_sc = sd->stride_c; p.x_st = sd->stride_t; p.x_sk = sd->stride_f;
+        p.B = batch; p.C = channels; p.T = frames; p.n_fft = plan->n_fft; p.hop = plan->hop; p.win = plan->win;
+        p.out_len = (int)out_len; p.dualn = plan->dualn; p.tw = plan->tw;
+        p.y = y_dev; p.y_sb = yd->stride_b; p.y_sc = yd->stride_c; p.y_sl = yd->stride_l;
+        p.n_warps = 8; p.n_tiles_s = (int)((out_len + 255) / 256);
+        const int smem = plan->n_fft * 8;
+        if (smem > plan->dev.smem_optin) return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft too large");
+        if ((rc = kb_set_smem(kb_idft_kernel, smem))) return rc;
+        long long tiles = (long long)batch * channels * p.n_tiles_s;
+        int grid = (int)(tiles < plan->dev.sm_count * 8LL ? tiles : plan->dev.sm_count * 8LL);
+        kb_idft_kernel<<<grid, 256, smem, st>>>(p);
+        KB_CUDA(cudaGetLastError());
+        g_launches++;
+        return 0;
+    }
+
+    const int Q = plan->Q, FPW = 32 / Q;
+    const int R = (plan->win + plan->hop - 1) / plan->hop;
+    // one FFT round per overlap class: TFc = R * NW * FPW frames per tile
+    int NW = kb_env_int("KAPRE_B200_INW", 4), TFc = 0, smem = 0, bps = 0;
+    for (;; NW >>= 1) {
+        if (NW < 1) return kb_fail(KAPRE_E_UNSUPPORTED, "inverse STFT tile does not fit shared memory (n_fft=%d hop=%d)", plan->n_fft, plan->hop);
+        TFc = R * NW * FPW;
+        if (TFc < R) TFc = R;
+        const KbIstftSmem L = kb_istft_smem_layout(Q, plan->n_fft, plan->hop, plan->win, TFc, NW);
+        smem = L.total;
+        if (smem <= plan->dev.smem_optin) break;
+    }
+    bps = (228 * 1024) / (smem + 1024);
+    if (bps > 64 / NW) bps = 64 / NW;
+    if (bps < 1) bps = 1;
+    KbIstftParams p{};
+    p.X = (const float2*)stft_dev; p.x_sb = sd->stride_b; p.x_sc = sd->stride_c; p.x_st = sd->stride_t; p.x_sk = sd->stride_f;
+    p.B = batch; p.C = channels; p.T = frames; p.n_fft = plan->n_fft; p.hop = plan->hop; p.win = plan->win;
+    p.out_len = (int)out_len; p.dual = plan->dual; p.twp = plan->twp; p.twn = plan->twn;
+    p.y = y_dev; p.y_sb = yd->stride_b; p.y_sc = yd->stride_c; p.y_sl = yd->stride_l;
+    p.TFc = TFc; p.R = R; p.hops_out = TFc - (R - 1);
+    p.n_tiles_t = kb_istft_tiles(frames, plan->hop, plan->win_length, p.hops_out);
+    p.n_warps = NW;
+    const long long tiles = (long long)batch * channels * p.n_tiles_t;
+    if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
+    const long long gmax = (long long)plan->dev.sm_count * bps;
+    const int grid = (int)(tiles < gmax ? tiles : gmax);
+    switch (Q) {
+        case 4: rc = kb_launch_istft<4>(p, grid, smem, st); break;
+        case 8: rc = kb_launch_istft<8>(p, grid, smem, st); break;
+        case 16: rc = kb_launch_istft<16>(p, grid, smem, st); break;
+        case 32: rc = kb_launch_istft<32>(p, grid, smem, st); break;
+        default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+    }
+    return rc;
+}
+
+int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre_filterbank** out) {
+    if (!out || !fb_host) return kb_fail(KAPRE_E_INVALID, "null argument");
+    if (n_freq < 1 || n_bands < 1) return kb_fail(KAPRE_E_INVALID, "empty filterbank");
+    kapre_filterbank* f = new kapre_filterbank();
+    f->n_freq = n_freq; f->n_bands = n_bands;
+    int rc = kb_dev_info(&f->dev);
+    if (rc) { delete f; return rc; }
+    std::vector<KbBand> bands; std::vector<float> w;
+    kb_make_bands(fb_host, n_freq, n_bands, bands, w);
+    if ((rc = kb_upload(bands, &f->bands)) || (rc = kb_upload(w, &f->w))) { kapre_filterbank_destroy(f); return rc; }
+    *out = f;
+    return 0;
+}
+
+void kapre_filterbank_destroy(kapre_filterbank* f) {
+    if (!f) return;
+    cudaFree(f->bands); cudaFree(f->w);
+    delete f;
+}
+
+int kapre_apply_filterbank(const kapre_filterbank* fb, const float* x_dev, int batch, int channels, int frames,
+                           const kapre_spec_desc* xd, float* out_dev, const kapre_spec_desc* od, void* stream) {
+    if (!fb || !xd || !od) return kb_fail(KAPRE_E_INVALID, "null argument");
+    int rc = kb_check_device(fb->dev);
+    if (rc) return rc;
+    if (batch < 0 || channels < 0 || frames < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    if (batch == 0 || channels == 0 || frames == 0) return 0;
+    if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    KbFbParams p{};
+    p.x = x_dev; p.x_sb = xd->stride_b; p.x_sc = xd->stride_c; p.x_st = xd->stride_t; p.x_sk = xd->stride_f;
+    p.B = batch; p.C = channels; p.T = frames; p.F = fb->n_freq;
+    p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands;
+    p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
+    p.n_tiles_t = (frames + 31) / 32; p.n_warps = 8;
+    const KbFbSmem L = kb_fb_smem_layout(fb->n_freq, fb->n_bands);
+    if (L.total > fb->dev.smem_optin)
+        return kb_fail(KAPRE_E_UNSUPPORTED, "filterbank %dx%d does not fit shared memory", fb->n_freq, fb->n_bands);
+    if ((rc = kb_set_smem(kb_fb_kernel, L.total))) return rc;
+    int bps = (228 * 1024) / (L.total + 1024);
+    if (bps > 8) bps = 8;
+    if (bps < 1) bps = 1;
+    const long long tiles = (long long)batch * channels * p.n_tiles_t;
+    const long long gmax = (long long)fb->dev.sm_count * bps;
+    const int grid = (int)(tiles < gmax ? tiles : gmax);
+    kb_fb_kernel<<<grid, 256, L.total, (cudaStream_t)stream>>>(p);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+static int kb_ew_grid(int64_t n, int* grid) {
+    int dev = 0, sms = 0;
+    KB_CUDA(cudaGetDevice(&dev));
+    KB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long g = (n + 255) / 256;
+    const long long cap = (long long)sms * 16;
+    *grid = (int)(g < cap ? g : cap);
+    if (*grid < 1) *grid = 1;
+    return 0;
+}
+
+int kapre_magnitude(const void* x_complex_dev, float* out_dev, int64_t n, void* stream) {
+    if (n < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    if (n == 0) return 0;
+    if (!x_complex_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    int grid, rc;
+    if ((rc = kb_ew_grid(n, &grid))) return rc;
+    kb_magnitude_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)x_complex_dev, out_dev, n);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+int kapre_phase(const void* x_complex_dev, float* out_dev, int64_t n, void* stream) {
+    if (n < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    if (n == 0) return 0;
+    if (!x_complex_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    int grid, rc;
+    if ((rc = kb_ew_grid(n, &grid))) return rc;
+    kb_phase_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)x_complex_dev, out_dev, n);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_items, int64_t item_size,
+                               const kapre_db_cfg* db, void* workspace_dev, void* stream) {
+    int rc = kb_check_db(db);
+    if (rc) return rc;
+    if (n_items < 0 || item_size < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    if (n_items == 0 || item_size == 0) return 0;
+    if (!x_dev || !out_dev || !workspace_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float db_mul, db_sub;
+    kb_db_consts(db, &db_mul, &db_sub);
+    long long chunks = (item_size + 256 * 8 - 1) / (256 * 8);
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    const long long grid = n_items * chunks;
+    if (grid > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items");
+    KB_CUDA(cudaMemsetAsync(workspace_dev, 0, (size_t)n_items * 4, st));
+    kb_db_kernel<<<(unsigned)grid, 256, 0, st>>>(x_dev, out_dev, item_size, (int)chunks, (unsigned int*)workspace_dev,
+                                                 db->amin, db_mul, db_sub);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return kb_launch_clamp(out_dev, n_items, item_size, (const unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
+                           db->dynamic_range, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// kapre_b200 -- shared host/device definitions for the STFT hot path.
+//
+// The kernel bodies in stft_core.cuh / istft_core.cuh are written as sequences of
+// barrier-free "phases".  Under nvcc each phase runs once per CUDA thread and phases are
+// separated by __syncwarp()/__syncthreads(); under a plain host compiler (KB_HOST_EMU, used
+// only by tests/emu to validate the index arithmetic without a GPU) each phase is a loop
+// over all threads of the CTA, which is a legal serialisation of the same program.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KB_HD __host__ __device__ __forceinline__
+#define KB_D __device__ __forceinline__
+#else
+#define KB_HD inline
+#define KB_D inline
+#include <cmath>
+#include <cstring>
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+#endif
+
+#define KB_MAX_WARPS 8
+
+// ---- output modes of the fused forward kernel -------------------------------------------
+enum KbMode {
+    KB_OUT_COMPLEX = 0,  // complex64 STFT            (kapre.STFT)
+    KB_OUT_MAG = 1,      // |STFT|                    (STFT -> Magnitude)
+    KB_OUT_MAG_DB = 2,   // dB(|STFT|), unclamped     (... -> MagnitudeToDecibel)
+    KB_OUT_FB = 3,       // filterbank(|STFT|)        (... -> ApplyFilterbank)
+    KB_OUT_FB_DB = 4,    // dB(filterbank(|STFT|))    (get_melspectrogram_layer(return_decibel))
+};
+
+// Filterbank in "banded" form: band m covers bins [lo, hi) with weights w[off + (k - lo)].
+struct KbBand { int lo, hi, off, pad; };
+
+struct KbStftParams {
+    // input waveform, element strides (batch, channel, sample)
+    const float* x;
+    long long x_sb, x_sc, x_sl;
+    int B, C, L;
+    // transform
+    int n_fft, hop, T;   // T = number of frames per (batch, channel)
+    int pad_left;        // zeros prepended (n_fft - hop if pad_begin)  kapre/time_frequency.py:169-172
+    // tables (device): wh = 0.5 * window zero-padded / cropped to n_fft;
+    // twp[q*33 + k1] = exp(-2 pi i q k1 / P); twn[k] = exp(-2 pi i k / n_fft), k < P/2 (P = n_fft/2)
+    const float* wh;
+    const float2* twp;
+    const float2* twn;
+    // output, element strides (batch, channel, frame, bin)
+    void* out;
+    long long o_sb, o_sc, o_st, o_sk;
+    int mode;
+    // filterbank (modes FB / FB_DB)
+    const KbBand* bands;
+    const float* fbw;
+    int n_bands;
+    // decibel (modes *_DB): y = db_mul * log2(max(v, amin)) - db_sub; per-item max of max(v, amin)
+    float amin, db_mul, db_sub;
+    unsigned int* item_max;  // B entries, uint view of non-negative floats, zero-initialised
+    // tiling
+    int TF;          // frames per tile
+    int n_tiles_t;   // ceil(T / TF)
+    int n_warps;     // warps per CTA
+};
+
+struct KbIstftParams {
+    const float2* X;                     // complex STFT, element strides (batch, channel, frame, bin)
+    long long x_sb, x_sc, x_st, x_sk;
+    int B, C, T;
+    int n_fft, hop, win;                 // win = min(win_length, n_fft) samples kept per frame
+    int out_len;                         // (T-1)*hop + win_length
+    const float* dual;                   // dual window / P scaling folded in, length win (device)
+    const float2* twp;
+    const float2* twn;
+    float* y;                            // element strides (batch, channel, sample)
+    long long y_sb, y_sc, y_sl;
+    int TFc;                             // frames computed per tile (incl. halo)
+    int R;                               // overlap classes = ceil(win / hop)
+    int hops_out;                        // output hops per tile = TFc - (R - 1)
+    int n_tiles_t;
+    int n_warps;
+};
+
+struct cpx { float re, im; };
+KB_HD cpx cmake(float a, float b) { cpx r; r.re = a; r.im = b; return r; }
+KB_HD cpx cadd(cpx a, cpx b) { return cmake(a.re + b.re, a.im + b.im); }
+KB_HD cpx csub(cpx a, cpx b) { return cmake(a.re - b.re, a.im - b.im); }
+KB_HD cpx cmul(cpx a, cpx b) { return cmake(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+
+// shared-memory footprint helpers (bytes), shared by host launch code and kernels
+KB_HD int kb_align16(int v) { return (v + 15) & ~15; }

@@ -1,0 +1,82 @@
+// Host-side builders for the constant tables the kernels read (window, twiddles, banded
+// filterbank, dual window).  Pure C++ (no CUDA) so the CPU emulation harness in tests/emu
+// shares them with the CUDA library.
+#pragma once
+#include <cmath>
+#include <vector>
+#include "kb_common.h"
+
+static inline int kb_q_for_nfft(int n_fft) {
+    // supported fast-path sizes: n_fft = 64 * Q, Q in {4, 8, 16, 32}
+    switch (n_fft) {
+        case 256: return 4;
+        case 512: return 8;
+        case 1024: return 16;
+        case 2048: return 32;
+        default: return 0;
+    }
+}
+
+// exp(-2 pi i q k1 / P), row stride 33 (bank-conflict padding)
+static inline void kb_make_twp(int Q, std::vector<float2>& out) {
+    const int P = 32 * Q;
+    out.assign((size_t)Q * 33, make_float2(1.0f, 0.0f));
+    for (int q = 0; q < Q; ++q)
+        for (int k1 = 0; k1 < 32; ++k1) {
+            const int r = (q * k1) % P;
+            const double a = -2.0 * M_PI * (double)r / (double)P;
+            out[(size_t)q * 33 + k1] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+}
+
+// exp(-2 pi i k / n_fft), k = 0 .. n_fft/4 - 1
+static inline void kb_make_twn(int n_fft, std::vector<float2>& out) {
+    const int n = n_fft / 4;
+    out.resize(n);
+    for (int k = 0; k < n; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)n_fft;
+        out[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+}
+
+// 0.5 * analysis window, right zero-padded (win < n_fft) or cropped (win > n_fft) to n_fft:
+// tf.signal.stft's rfft(fft_length) semantics, kapre/time_frequency.py:174-182.  The 0.5 is
+// the (Z[k] +- conj Z[P-k]) / 2 of the packed real FFT, folded in here (exact in binary fp).
+static inline void kb_make_wh(const float* window, int win_length, int n_fft, std::vector<float>& out) {
+    out.assign(n_fft, 0.0f);
+    const int n = win_length < n_fft ? win_length : n_fft;
+    for (int i = 0; i < n; ++i) out[i] = 0.5f * window[i];
+}
+
+// Banded form of a (n_freq x n_bands) row-major filterbank: per band the tight support
+// [lo, hi) of its non-zero weights (interior zeros kept).
+static inline void kb_make_bands(const float* fb, int n_freq, int n_bands,
+                                 std::vector<KbBand>& bands, std::vector<float>& w) {
+    bands.resize(n_bands);
+    w.clear();
+    for (int m = 0; m < n_bands; ++m) {
+        int lo = n_freq, hi = 0;
+        for (int k = 0; k < n_freq; ++k)
+            if (fb[(size_t)k * n_bands + m] != 0.0f) {
+                if (k < lo) lo = k;
+                hi = k + 1;
+            }
+        if (hi <= lo) { lo = 0; hi = 0; }
+        KbBand b;
+        b.lo = lo; b.hi = hi; b.off = (int)w.size(); b.pad = 0;
+        for (int k = lo; k < hi; ++k) w.push_back(fb[(size_t)k * n_bands + m]);
+        bands[m] = b;
+    }
+    if (w.empty()) w.push_back(0.0f);
+}
+
+// Synthesis-window table for the inverse kernel: dual[m] = w~[m] / n_fft, negated for odd m
+// (x[2n+1] = -Im FFT(conj Z)[n] / N); w~ is tf.signal.inverse_stft_window_fn's window,
+// kapre/time_frequency.py:278-280, truncated to the samples irfft(n_fft) actually provides.
+static inline void kb_make_dual(const float* dual_window, int win, int n_fft, std::vector<float>& out) {
+    out.assign(win + 2, 0.0f);
+    for (int m = 0; m < win; ++m) {
+        const double v = (double)dual_window[m] / (double)n_fft;
+        out[m] = (float)((m & 1) ? -v : v);
+    }
+}

@@ -1,0 +1,95 @@
+// CPU emulation harness for the CUDA kernel bodies (tests only, never shipped).
+// Compiles kapre_b200/csrc/*_core.cuh with KB_HOST_EMU so every barrier-free phase runs as a
+// loop over the CTA's threads; lets `pytest -m "not gpu"` validate the index arithmetic of
+// the fused kernels against the oracle in a container that has no GPU.
+#define KB_HOST_EMU 1
+#include <cstdio>
+#include <vector>
+#include "../../kapre_b200/csrc/kb_tables.h"
+#include "../../kapre_b200/csrc/stft_core.cuh"
+#include "../../kapre_b200/csrc/istft_core.cuh"
+
+template <int Q>
+static void run_stft(const KbStftParams& p, int n_cta) {
+    const KbStftSmem L = kb_stft_smem_layout(Q, p.n_fft, p.hop, p.TF, p.n_warps, p.mode, p.n_bands);
+    std::vector<char> smem(L.total + 64);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(smem.begin(), smem.end(), (char)0x7f);  // poison: catches reads of unwritten smem
+        kb_stft_cta<Q>(p, smem.data(), cta, n_cta);
+    }
+}
+
+template <int Q>
+static void run_istft(const KbIstftParams& p, int n_cta) {
+    const KbIstftSmem L = kb_istft_smem_layout(Q, p.n_fft, p.hop, p.win, p.TFc, p.n_warps);
+    std::vector<char> smem(L.total + 64);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(smem.begin(), smem.end(), (char)0x7f);
+        kb_istft_cta<Q>(p, smem.data(), cta, n_cta);
+    }
+}
+
+extern "C" {
+
+int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, int B, int C, int L,
+                int n_fft, int win_length, int hop, int pad_left, int T, const float* window,
+                int mode, void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk,
+                const float* fb, int n_freq, int n_bands, float amin, float db_mul, float db_sub,
+                unsigned int* item_max, int TF, int n_warps, int n_cta) {
+    const int Q = kb_q_for_nfft(n_fft);
+    if (!Q) return -1;
+    std::vector<float> wh;
+    std::vector<float2> twp, twn;
+    std::vector<KbBand> bands;
+    std::vector<float> fbw;
+    kb_make_wh(window, win_length, n_fft, wh);
+    kb_make_twp(Q, twp);
+    kb_make_twn(n_fft, twn);
+    if (fb) kb_make_bands(fb, n_freq, n_bands, bands, fbw);
+    KbStftParams p{};
+    p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
+    p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left;
+    p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data();
+    p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
+    p.bands = fb ? bands.data() : nullptr; p.fbw = fb ? fbw.data() : nullptr; p.n_bands = fb ? n_bands : 0;
+    p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max;
+    p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
+    switch (Q) {
+        case 4: run_stft<4>(p, n_cta); break;
+        case 8: run_stft<8>(p, n_cta); break;
+        case 16: run_stft<16>(p, n_cta); break;
+        case 32: run_stft<32>(p, n_cta); break;
+    }
+    return 0;
+}
+
+int kb_emu_istft(const float* X, long long x_sb, long long x_sc, long long x_st, long long x_sk,
+                 int B, int C, int T, int n_fft, int win_length, int hop, const float* dual_window,
+                 float* y, long long y_sb, long long y_sc, long long y_sl, int TFc, int n_warps, int n_cta) {
+    const int Q = kb_q_for_nfft(n_fft);
+    if (!Q) return -1;
+    std::vector<float> dual;
+    std::vector<float2> twp, twn;
+    const int win = win_length < n_fft ? win_length : n_fft;
+    kb_make_dual(dual_window, win, n_fft, dual);
+    kb_make_twp(Q, twp);
+    kb_make_twn(n_fft, twn);
+    KbIstftParams p{};
+    p.X = reinterpret_cast<const float2*>(X); p.x_sb = x_sb; p.x_sc = x_sc; p.x_st = x_st; p.x_sk = x_sk;
+    p.B = B; p.C = C; p.T = T; p.n_fft = n_fft; p.hop = hop; p.win = win;
+    p.out_len = (T - 1) * hop + win_length;
+    p.dual = dual.data(); p.twp = twp.data(); p.twn = twn.data();
+    p.y = y; p.y_sb = y_sb; p.y_sc = y_sc; p.y_sl = y_sl;
+    p.TFc = TFc; p.R = (win + hop - 1) / hop; p.hops_out = TFc - (p.R - 1);
+    p.n_tiles_t = kb_istft_tiles(T, hop, win_length, p.hops_out);
+    p.n_warps = n_warps;
+    switch (Q) {
+        case 4: run_istft<4>(p, n_cta); break;
+        case 8: run_istft<8>(p, n_cta); break;
+        case 16: run_istft<16>(p, n_cta); break;
+        case 32: run_istft<32>(p, n_cta); break;
+    }
+    return 0;
+}
+
+}  // extern "C"

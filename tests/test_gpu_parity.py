@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the float64 oracle and the
+committed golden fixtures.  Tolerances are written next to each assertion; the reference's own
+tolerances (tests/test_time_frequency.py:65-69,120,256,265-267,486; tests/test_backend.py:12,40)
+are asserted as well where a reference test is mirrored."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+import oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def K():
+    assert torch.cuda.is_available(), 'GPU tier needs a CUDA device'
+    import kapre_b200
+    from kapre_b200 import _native
+    _native.lib()  # the CUDA library must be the thing that runs: fail loudly if it is missing
+    return kapre_b200
+
+
+def nerr(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(float(np.abs(b).max()), 1e-30))
+
+
+def wave(rng, B, C, L, fmt):
+    shape = (B, C, L) if fmt == 'channels_first' else (B, L, C)
+    return rng.uniform(-1, 1, size=shape).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------- STFT
+@pytest.mark.parametrize('n_fft,win,hop', [(256, 256, 64), (512, 512, 256), (1024, 1024, 256), (2048, 2048, 1024),
+                                           (2048, 2018, 1024), (1024, 400, 160), (512, 512, 125), (1000, 1000, 250),
+                                           (1000, 512, 256), (96, 96, 24)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('pad', [(False, False), (True, True)])
+def test_stft_complex_vs_oracle(K, n_fft, win, hop, fmt, pad):
+    rng = np.random.default_rng(n_fft + hop)
+    x = wave(rng, 3, 2, 6000, fmt)
+    layer = K.STFT(n_fft=n_fft, win_length=win, hop_length=hop, pad_begin=pad[0], pad_end=pad[1],
+                   input_data_format=fmt, output_data_format=fmt)
+    got = layer(x)  # numpy in -> numpy out
+    ref = O.stft_layer(x, n_fft, win, hop, None, pad[0], pad[1], fmt, fmt)
+    assert got.shape == ref.shape and got.dtype == np.complex64
+    assert nerr(got, ref) < 2e-6  # fp32 FFT vs float64 truth, normalised max-abs
+
+
+@pytest.mark.parametrize('ifmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('ofmt', ['channels_first', 'channels_last'])
+def test_stft_mixed_formats(K, ifmt, ofmt):
+    rng = np.random.default_rng(5)
+    x = wave(rng, 2, 3, 5000, ifmt)
+    got = K.STFT(n_fft=512, hop_length=128, input_data_format=ifmt, output_data_format=ofmt)(x)
+    ref = O.stft_layer(x, 512, None, 128, None, False, False, ifmt, ofmt)
+    assert got.shape == ref.shape
+    assert nerr(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize('wname', [None, 'hann_window', 'hamming_window'])
+def test_stft_windows_golden(K, golden, wname):
+    """Mirror of tests/test_time_frequency.py:128-185 on the reference's speech fixture."""
+    src = golden['audio']
+    x = np.tile(src[None, :, None], (1, 1, 2))
+    got = K.STFT(n_fft=512, win_length=512, hop_length=256, window_name=wname, input_data_format='channels_last',
+                 output_data_format='channels_last')(x)[0]
+    ref = golden['stft_512_256_%s' % (wname or 'hann_window')]
+    for ch in range(2):
+        g = got[:, :, ch]
+        np.testing.assert_allclose(np.abs(g), np.abs(ref), rtol=1e-5, atol=1e-3)   # reference tolerance
+        np.testing.assert_allclose(g.real, ref.real, rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(g.imag, ref.imag, rtol=1e-5, atol=1e-3)
+        assert nerr(g, ref) < 2e-6                                                # ours
+
+
+@pytest.mark.parametrize('hop', [250, 256])
+@pytest.mark.parametrize('n_ch', [1, 2, 6])
+@pytest.mark.parametrize('fmt', ['default', 'channels_first', 'channels_last'])
+@pytest.mark.parametrize('batch', [1, 10])
+def test_spectrogram_correctness_n1000(K, golden, hop, n_ch, fmt, batch):
+    """Mirror of tests/test_time_frequency.py:72-125 (n_fft=1000: the direct-DFT kernel)."""
+    src = golden['audio']
+    x = np.tile(src[None, :, None], (batch, 1, n_ch))
+    if fmt == 'channels_first':
+        x = np.ascontiguousarray(np.transpose(x, (0, 2, 1)))
+    got = K.STFT(n_fft=1000, win_length=1000, hop_length=None if hop == 250 else hop, input_data_format=fmt,
+                 output_data_format=fmt)(x)[0]
+    ref = golden['stft_1000_%d_default' % hop]
+    ref = np.tile(ref[:, :, None], (1, 1, n_ch))
+    if fmt == 'channels_first':
+        ref = np.transpose(ref, (2, 0, 1))
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(np.abs(got), np.abs(ref), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(got.real, ref.real, rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(got.imag, ref.imag, rtol=1e-5, atol=1e-3)
+    assert nerr(got, ref) < 5e-6
+    mag = K.Sequential([K.STFT(n_fft=1000, hop_length=hop, input_data_format=fmt, output_data_format=fmt),
+                        K.Magnitude()])(x)[0]
+    np.testing.assert_allclose(np.abs(ref), mag, atol=2e-4)
+    ph = K.Sequential([K.STFT(n_fft=1000, hop_length=hop, input_data_format=fmt, output_data_format=fmt),
+                       K.Phase()])(x)[0]
+    np.testing.assert_allclose(np.sin(np.angle(got)), np.sin(ph), atol=1e-3)
+    np.testing.assert_allclose(np.cos(np.angle(got)), np.cos(ph), atol=1e-3)
+
+
+@pytest.mark.parametrize('pad_end', [False, True])
+def test_stft_short_window_golden(K, golden, pad_end):
+    """win_length < n_fft is RIGHT zero-padded (tests/test_time_frequency.py:270-357)."""
+    x = golden['audio'][None, :, None]
+    got = K.STFT(n_fft=1000, win_length=512, hop_length=250, pad_end=pad_end, input_data_format='channels_last',
+                 output_data_format='channels_last')(x)[0, :, :, 0]
+    ref = golden['stft_1000_250_win512_padend%d' % pad_end]
+    assert got.shape == ref.shape
+    assert nerr(got, ref) < 5e-6
+
+
+# ------------------------------------------------------------------------------- fused magnitude / mel / dB
+@pytest.mark.parametrize('n_fft,hop,n_mels,sr', [(512, 256, 64, 16000), (1024, 256, 128, 22050), (2048, 512, 128, 44100),
+                                                  (256, 128, 20, 8000), (1024, 160, 80, 16000)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_melspectrogram_fused_vs_oracle(K, n_fft, hop, n_mels, sr, fmt):
+    rng = np.random.default_rng(n_fft)
+    x = wave(rng, 3, 2, 9000, fmt)
+    x[1] *= 1e-3  # a quiet item: the per-item maximum must not leak between items
+    kw = dict(n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels, input_data_format=fmt, output_data_format=fmt)
+    xt = torch.from_numpy(x).cuda()
+    mel = K.get_melspectrogram_layer(**kw)(xt).cpu().numpy()
+    ref = O.melspectrogram_layer(x, **kw)
+    assert mel.shape == ref.shape
+    assert nerr(mel, ref) < 2e-6
+    # fused == layer-by-layer (stand-alone kernels) to rounding
+    seq = K.get_melspectrogram_layer(**kw)
+    y = xt
+    for layer in seq.layers:
+        y = layer(y)
+    assert nerr(y.cpu().numpy(), ref) < 2e-6
+    # decibel, default dynamic range (clamp inactive for the loud items, active nowhere)
+    db = K.get_melspectrogram_layer(return_decibel=True, **kw)(xt).cpu().numpy()
+    refdb = O.melspectrogram_layer(x, return_decibel=True, **kw)
+    assert np.abs(db - refdb).max() < 2e-4  # dB, absolute (fp32 mel of ~1e-7 relative -> ~1e-5 dB; log2 approx)
+    np.testing.assert_allclose(refdb, db, rtol=3e-3)  # reference tolerance, test_time_frequency.py:265-267
+
+
+@pytest.mark.parametrize('amin', [1e-5, 1e-3])
+@pytest.mark.parametrize('dynamic_range', [120.0, 80.0])
+@pytest.mark.parametrize('fmt', ['default', 'channels_first', 'channels_last'])
+@pytest.mark.parametrize('hop', [128, 256])
+def test_melspectrogram_correctness_golden(K, golden, amin, dynamic_range, fmt, hop):
+    """Mirror of tests/test_time_frequency.py:188-267 (the reference's primary parity test)."""
+    src = golden['audio']
+    x = np.tile(src[None, :, None], (1, 1, 2))
+    if fmt == 'channels_first':
+        x = np.ascontiguousarray(np.transpose(x, (0, 2, 1)))
+
+    def shape_ref(r):
+        r = np.tile(r[:, :, None], (1, 1, 2))
+        return np.transpose(r, (2, 0, 1)) if fmt == 'channels_first' else r
+
+    kw = dict(n_fft=512, sample_rate=22050, n_mels=40, mel_f_min=0.0, mel_f_max=8000, win_length=512,
+              hop_length=None if hop == 128 else hop, input_data_format=fmt, output_data_format=fmt)
+    S = K.get_melspectrogram_layer(return_decibel=False, **kw).predict(x)[0]
+    S_ref = shape_ref(golden['mel_512_%d' % hop])
+    np.testing.assert_allclose(S_ref, S, atol=1e-4)          # reference tolerance (:256)
+    assert nerr(S, S_ref) < 2e-6
+    Sdb = K.get_melspectrogram_layer(return_decibel=True, db_amin=amin, db_dynamic_range=dynamic_range, **kw).predict(x)[0]
+    Sdb_ref = shape_ref(golden['meldb_512_%d_amin%g_dr%g' % (hop, amin, dynamic_range)])
+    np.testing.assert_allclose(Sdb_ref, Sdb, rtol=3e-3)      # reference tolerance (:265-267)
+    assert np.abs(Sdb - Sdb_ref).max() < 2e-4
+
+
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_stft_magnitude_db_and_clamp(K, fmt):
+    """get_stft_magnitude_layer(return_decibel=True) incl. a case where the dynamic-range clamp
+    binds (full-scale sine, n_fft=2048: peak ~ +30 dB, floor -50 dB, range 60 dB)."""
+    rng = np.random.default_rng(3)
+    B, C, L = 3, 2, 12000
+    t = np.arange(L) / 16000.0
+    x = np.zeros((B, C, L), np.float32)
+    x[0] = np.sin(2 * np.pi * 1000.0 * t)[None, :]            # loud tone -> clamp binds
+    x[1] = 1e-4 * rng.uniform(-1, 1, size=(C, L))             # quiet -> amin floor
+    x[2, 0] = rng.uniform(-1, 1, size=L)                      # one loud channel sets the item max ...
+    x[2, 1] = 1e-6 * rng.uniform(-1, 1, size=L)               # ... the other one gets clamped by it
+    if fmt == 'channels_last':
+        x = np.ascontiguousarray(np.transpose(x, (0, 2, 1)))
+    kw = dict(n_fft=2048, hop_length=512, return_decibel=True, db_dynamic_range=60.0, input_data_format=fmt,
+              output_data_format=fmt)
+    got = K.get_stft_magnitude_layer(**kw)(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.stft_magnitude_layer(x, **kw)
+    assert got.shape == ref.shape
+    # the clamp must actually have been exercised
+    unclamped = O.stft_magnitude_layer(x, **dict(kw, db_dynamic_range=1e9))
+    assert (np.abs(ref - unclamped) > 1.0).any()
+    # fp32 rounding noise sits far below the clamp threshold (peak - 60 dB), so after the clamp
+    # the whole tensor is comparable: 5e-3 dB absolute
+    assert np.abs(got - ref).max() < 5e-3
+
+
+@pytest.mark.parametrize('dynamic_range', [80.0, 120.0])
+def test_magnitude_to_decibel_literal(K, golden, dynamic_range):
+    """Mirror of tests/test_backend.py:15-40 (per-row maximum)."""
+    x = golden['db_literal_in'].astype(np.float32)
+    got = K.backend.magnitude_to_decibel(x, ref_value=1.0, amin=1e-5, dynamic_range=dynamic_range)
+    np.testing.assert_allclose(got, golden['db_literal_dr%g' % dynamic_range], atol=1e-5)  # reference TOL
+    got1d = K.backend.magnitude_to_decibel(x[1], ref_value=1.0, amin=1e-5, dynamic_range=dynamic_range)
+    np.testing.assert_allclose(got1d, golden['db_literal_dr%g' % dynamic_range][1], atol=1e-5)
+    with pytest.raises(ValueError):
+        K.backend.magnitude_to_decibel(x, amin=0.0)
+    with pytest.raises(ValueError):
+        K.MagnitudeToDecibel(dynamic_range=-1.0)(torch.from_numpy(x).cuda())
+
+
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('kind', ['mel', 'log'])
+def test_apply_filterbank_standalone(K, fmt, kind):
+    rng = np.random.default_rng(11)
+    B, C, T, F = 2, 3, 45, 513
+    shape = (B, C, T, F) if fmt == 'channels_first' else (B, T, F, C)
+    x = rng.uniform(0, 10, size=shape).astype(np.float32)
+    if kind == 'mel':
+        kwargs = {'sample_rate': 22050, 'n_freq': F, 'n_mels': 96, 'f_min': 30.0, 'f_max': 9000.0, 'htk': True, 'norm': None}
+        fb = O.filterbank_mel(22050, F, 96, 30.0, 9000.0, True, None)
+    else:
+        kwargs = {'sample_rate': 22050, 'n_freq': F, 'n_bins': 84, 'bins_per_octave': 12, 'f_min': None, 'spread': 0.125}
+        fb = O.filterbank_log(22050, F, 84, 12)
+    layer = K.ApplyFilterbank(type=kind, filterbank_kwargs=kwargs, data_format=fmt)
+    np.testing.assert_allclose(layer.filterbank, fb, rtol=1e-6, atol=1e-9)
+    got = layer(x)
+    ref = O.apply_filterbank(x.astype(np.float64), fb.astype(np.float64), fmt)
+    assert got.shape == ref.shape
+    assert nerr(got, ref) < 2e-6
+
+
+def test_log_frequency_layer_fused(K):
+    rng = np.random.default_rng(12)
+    x = wave(rng, 2, 1, 8000, 'channels_last')
+    seq = K.get_log_frequency_spectrogram_layer(n_fft=1024, hop_length=256, return_decibel=True)
+    got = seq(torch.from_numpy(x).cuda()).cpu().numpy()
+    s = np.abs(O.stft_layer(x, 1024, None, 256))
+    ref = O.magnitude_to_decibel(O.apply_filterbank(s, O.filterbank_log(22050, 513).astype(np.float64), 'default'))
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 5e-4
+
+
+# ------------------------------------------------------------------------------- inverse STFT
+@pytest.mark.parametrize('n_fft,win,hop', [(1024, 1024, 256), (2048, 2048, 1024), (2048, 2048, 256), (512, 400, 100),
+                                           (256, 256, 64), (1000, 1000, 250), (1000, 600, 200)])
+@pytest.mark.parametrize('ifmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('ofmt', ['channels_first', 'channels_last'])
+def test_istft_vs_oracle(K, n_fft, win, hop, ifmt, ofmt):
+    rng = np.random.default_rng(n_fft + hop)
+    B, C, T, F = 2, 2, 41, n_fft // 2 + 1
+    shape = (B, C, T, F) if ifmt == 'channels_first' else (B, T, F, C)
+    X = (rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(np.complex64)
+    got = K.InverseSTFT(n_fft=n_fft, win_length=win, hop_length=hop, input_data_format=ifmt, output_data_format=ofmt)(X)
+    ref = O.istft_layer(X, n_fft, win, hop, None, ifmt, ofmt)
+    assert got.shape == ref.shape and got.dtype == np.float32
+    assert nerr(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize('wfmt', ['default', 'channels_first', 'channels_last'])
+@pytest.mark.parametrize('sfmt', ['default', 'channels_first', 'channels_last'])
+@pytest.mark.parametrize('hop_ratio', [0.5, 0.25, 0.125])
+def test_perfectly_reconstructing_stft_istft(K, golden, wfmt, sfmt, hop_ratio):
+    """Mirror of tests/test_time_frequency.py:447-486 (STFT -> ISTFT, atol 1e-5)."""
+    src = golden['audio']
+    x = src[None, :, None] if wfmt != 'channels_first' else src[None, None, :]
+    n_fft, hop = 2048, int(2048 * hop_ratio)
+    stft, istft = K.get_perfectly_reconstructing_stft_istft(n_fft, hop, wfmt, sfmt)
+    rec = K.Sequential([stft, istft])(x)
+    lead = n_fft - hop
+    rec = rec[:, :, lead:lead + 8000] if wfmt == 'channels_first' else rec[:, lead:lead + 8000, :]
+    np.testing.assert_allclose(x, rec, atol=1e-5)
+
+
+def test_cfg4_roundtrip_mse(K):
+    """BASELINE cfg4: batch 128 mono 16 kHz, n_fft 1024 hop 256, reconstruction error."""
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    x = torch.rand((128, 16000, 1), generator=g, device='cuda') * 2 - 1
+    stft, istft = K.get_perfectly_reconstructing_stft_istft(1024, 256, 'channels_last', 'channels_last')
+    y = istft(stft(x))
+    assert y.shape == (128, 17664, 1)
+    d = y[:, 768:768 + 16000, :] - x
+    assert float(d.abs().max()) < 5e-6 and float((d * d).mean()) < 1e-12
+
+
+# ------------------------------------------------------------------------------- full-size properties (cfg2)
+def test_cfg2_full_size_properties(K):
+    """BASELINE cfg2 (batch 256, 22.05 kHz x 5 s, n_fft 1024, hop 256, 128 mel): spot-check items
+    against the oracle, plus size-independent properties on the whole batch."""
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    x = torch.rand((256, 110250, 1), generator=g, device='cuda') * 2 - 1
+    mel = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128,
+                                     input_data_format='channels_last', output_data_format='channels_last')
+    y = mel(x)
+    assert y.shape == (256, 427, 128, 1)
+    assert bool(torch.isfinite(y).all())
+    for i in (0, 101, 255):
+        ref = O.melspectrogram_layer(x[i:i + 1].cpu().numpy(), n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128)
+        assert nerr(y[i:i + 1].cpu().numpy(), ref) < 2e-6
+    # homogeneity: mel(2x) == 2 mel(x) exactly (power-of-two scaling commutes with every fp32 op on the path)
+    assert torch.equal(mel(2.0 * x), 2.0 * y)
+    # batch sharding: any split of the batch gives bit-identical items (the multi-GPU contract)
+    parts = torch.cat([mel(x[:100]), mel(x[100:228]), mel(x[228:])], dim=0)
+    assert torch.equal(parts, y)
+    # time shift by one hop moves the frames by one
+    ys = mel(x[:8, 256:, :])
+    assert torch.equal(ys[:, :425], y[:8, 1:426])
+    # decibel path: monotone map of the linear path, clamp inactive (max-80 < floor) -> identical to formula
+    ydb = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128, return_decibel=True,
+                                     input_data_format='channels_last', output_data_format='channels_last')(x)
+    expect = 10.0 * torch.log10(torch.clamp(y.double(), min=1e-5))
+    assert float((ydb.double() - expect).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------- C ABI behaviour
+def test_abi_errors_and_config(K):
+    from kapre_b200 import _native, ops
+    with pytest.raises(_native.KapreNativeError):
+        ops.stft_forward(torch.zeros(1, 100, 1), K.STFT(n_fft=512).plan, 'channels_last', 'channels_last', False, False)
+    with pytest.raises(ValueError):
+        K.InverseSTFT(n_fft=512)(torch.zeros((1, 3, 100, 1), dtype=torch.complex64).cuda())  # wrong bin count
+    # too-short input -> zero frames, like tf.signal.frame
+    out = K.STFT(n_fft=512, hop_length=128)(torch.zeros(2, 100, 1).cuda())
+    assert out.shape == (2, 0, 257, 1)
+    # config round trip
+    m = K.get_melspectrogram_layer(n_fft=512, hop_length=128, n_mels=32, return_decibel=True)
+    m2 = K.Sequential.from_config(m.get_config())
+    x = torch.rand(2, 4000, 1).cuda()
+    assert torch.equal(m(x), m2(x))
+    n0 = _native.launch_count()
+    m(x)
+    assert _native.launch_count() - n0 == 2  # fused kernel + clamp kernel
