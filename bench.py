@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- mel frames/sec of the fused STFT -> |.| -> mel -> dB hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one pass of the hot path over one batch of synthetic waveforms.  Workload (N=1 and
+per rank for N>1, weak scaling): BASELINE.json configs[1] -- batch 256, mono, 22.05 kHz x 5 s,
+n_fft=1024, hop=256, 128 mel bands, decibel output, through ``get_melspectrogram_layer``.
+Rank 0 prints ONE JSON line (contract in the task statement):
+  value      frames/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        frames/s through the public ``predict`` call with pinned HOST buffers: H2D of the
+             waveforms and D2H of the log-mel tensor inside the timed region
+  roofline   achieved algorithmic GB/s of the fused kernel (CUDA events around the kernel
+             itself, recorded by the library) against the measured HBM copy bandwidth
+  cpu_baseline  the oracle's multi-threaded CPU port on the same workload, timed on rank 0
+``--impl reference`` times that CPU port alone (the reference itself needs TensorFlow + librosa,
+which are not installable here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(batch=256, length=110250, channels=1, sample_rate=22050, n_fft=1024, hop=256, n_mels=128)
+WORKLOAD = ('cfg2: batch=256 mono 22.05kHz 5s, n_fft=1024 hop=256 n_mels=128, '
+            'get_melspectrogram_layer(return_decibel=True), channels_last')
+N_SETS = 3  # rotating input/output sets: 3 x (113 MB in + 56 MB out) = 507 MB > 126 MB L2
+
+
+def frames_per_step():
+    return CFG['batch'] * CFG['channels'] * (1 + (CFG['length'] - CFG['n_fft']) // CFG['hop'])
+
+
+def algorithmic_bytes_per_step():
+    """every covered sample read once + every output written once (fp32)."""
+    T = 1 + (CFG['length'] - CFG['n_fft']) // CFG['hop']
+    covered = (T - 1) * CFG['hop'] + CFG['n_fft']
+    return CFG['batch'] * CFG['channels'] * (4 * covered + 4 * T * CFG['n_mels'])
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'MEASURED_PEAKS.json (measured copy bandwidth)'
+    except Exception:
+        return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while a region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                     'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                     'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                     'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._once()
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self._stop.clear()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        if self.nv is None:
+            return
+        self._once()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def cpu_port(threads=None):
+    import torch
+    from oracle.fast_cpu import MelSpectrogramCPU
+    if threads:
+        torch.set_num_threads(threads)
+    return MelSpectrogramCPU(n_fft=CFG['n_fft'], hop_length=CFG['hop'], sample_rate=CFG['sample_rate'],
+                             n_mels=CFG['n_mels'], return_decibel=True, input_data_format='channels_last',
+                             output_data_format='channels_last')
+
+
+def run_cpu(steps, warmup, budget_s):
+    """Times the CPU port: `steps` passes over the cfg2 batch (stops early once budget_s is spent)."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = cpu_port()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand((CFG['batch'], CFG['length'], CFG['channels']), generator=g) * 2 - 1
+    for _ in range(max(1, warmup)):
+        model(x)
+    done, t0 = 0, time.perf_counter()
+    while done < steps:
+        model(x)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=frames_per_step() * done / dt, unit='frames/s', cores=torch.get_num_threads(), kind='port',
+                sample='%d passes over the cfg2 batch (%d frames each), torch-CPU fp32 op-by-op port of the '
+                       'reference graph, %.1f s' % (done, frames_per_step(), dt)), dt / done
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    warmup = max(3, args.warmup)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        base, s_per_step = run_cpu(args.steps, warmup, budget_s=150.0)
+        line = {'impl': 'reference', 'metric': 'mel_frames_per_sec', 'value': base['value'], 'unit': 'frames/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': warmup, 'ms_per_step': s_per_step * 1e3,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic U(-1,1) waveforms', 'config': {'workload': WORKLOAD, 'device': 'host CPU'},
+                'cpu_baseline': base,
+                'e2e': {'value': base['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0,
+                'note': 'reference arm = the oracle CPU port (TensorFlow/librosa are not installed in this sandbox)'}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    import kapre_b200 as K
+    from kapre_b200 import _native
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _native.lib()
+    layer = K.get_melspectrogram_layer(n_fft=CFG['n_fft'], hop_length=CFG['hop'], sample_rate=CFG['sample_rate'],
+                                       n_mels=CFG['n_mels'], return_decibel=True, input_data_format='channels_last',
+                                       output_data_format='channels_last')
+    shape = (CFG['batch'], CFG['length'], CFG['channels'])
+    xs = []
+    for i in range(N_SETS):
+        g = torch.Generator(device=dev).manual_seed(1234 + rank * N_SETS + i)
+        xs.append(torch.rand(shape, generator=g, device=dev) * 2 - 1)
+    frames = frames_per_step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if world > 1:
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    # ---------------- device-resident throughput ------------------------------------------------
+    outs = [None] * N_SETS
+    for i in range(warmup):
+        outs[i % N_SETS] = layer(xs[i % N_SETS])
+    _native.profile_read()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    n0 = _native.launch_count()
+    _native.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for i in range(args.steps):
+        outs[i % N_SETS] = layer(xs[i % N_SETS])
+    e1.record()
+    barrier()
+    sampler.stop()
+    _native.profile_enable(False)
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    launches = _native.launch_count() - n0
+    kern_ms, kern_n = _native.profile_read()
+    ms_per_step = ms_total / args.steps
+    value = world * frames * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end to end through predict() with pinned host buffers ---------------------
+    xh = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    for i, t in enumerate(xh):
+        t.copy_(xs[i])
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        layer.predict(xh[i % 2])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        y_host = layer.predict(xh[i % 2])
+    torch.cuda.synchronize()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    e2e_value = world * frames * e2e_steps / e2e_s
+    h2d = xh[0].numel() * 4
+    d2h = int(y_host.size) * 4
+
+    # ---------------- parity spot check of what was timed ---------------------------------------
+    import oracle
+    import numpy as np
+    ref = oracle.melspectrogram_layer(xs[0][:2].cpu().numpy(), n_fft=CFG['n_fft'], hop_length=CFG['hop'],
+                                      sample_rate=CFG['sample_rate'], n_mels=CFG['n_mels'], return_decibel=True)
+    max_err_db = float(np.abs(outs[0][:2].cpu().numpy() - ref).max()) if outs[0] is not None else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    kernel_ms = kern_ms / max(kern_n, 1)
+    achieved = algorithmic_bytes_per_step() / (kernel_ms * 1e-3) / 1e9 if kern_n else None
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': (achieved / peak) if achieved else None, 'traffic': None, 'peak_source': peak_src,
+                'kernel': 'kb_stft_kernel<16, FB_DB> (fused frame+window+FFT+|.|+mel+dB)',
+                'kernel_ms': kernel_ms, 'kernel_launches_timed': kern_n,
+                'algorithmic_bytes_per_launch': algorithmic_bytes_per_step(),
+                'read_only_frac': (CFG['batch'] * 4.0 * ((1 + (CFG['length'] - CFG['n_fft']) // CFG['hop'] - 1) * CFG['hop'] + CFG['n_fft'])
+                                   / (kernel_ms * 1e-3) / 1e9 / peak) if kern_n else None}
+    traffic_file = os.path.join(ROOT, 'profiles', 'traffic_bytes_per_launch.json')
+    if os.path.exists(traffic_file):
+        try:
+            roofline['traffic'] = json.load(open(traffic_file)).get('cfg2_fb_db')
+        except Exception:
+            pass
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = run_cpu(steps=40, warmup=1, budget_s=12.0)
+    line = {
+        'metric': 'mel_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic U(-1,1) waveforms, generated on device (seeded)',
+        'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': frames, 'global_batch': CFG['batch'] * world,
+                   'parallelism': 'dp%d (batch sharded, no collective in the data path)' % world,
+                   'l2': '%d rotating input/output sets (%.0f MB) > 126 MB L2' % (
+                       N_SETS, N_SETS * algorithmic_bytes_per_step() / 1e6),
+                   'launch': _native.last_launch_info()},
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'steps': e2e_steps, 'api': 'Sequential.predict(pinned host tensor) -> host array'},
+        'gpu_launches': launches,
+        'clocks': sampler.summary(),
+        'max_abs_err_db_vs_oracle': max_err_db,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

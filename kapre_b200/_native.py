@@ -56,6 +56,8 @@ SYMBOLS = [
     ('kapre_version', c_int, []),
     ('kapre_launch_count', c_uint64, []),
     ('kapre_last_launch_info', c_char_p, []),
+    ('kapre_profile_enable', c_int, [c_int]),
+    ('kapre_profile_read', c_int, [POINTER(ctypes.c_double), POINTER(c_uint64)]),
 ]
 
 _lib = None
@@ -92,3 +94,14 @@ def launch_count() -> int:
 def last_launch_info() -> str:
     s = lib().kapre_last_launch_info()
     return s.decode() if s else ''
+
+
+def profile_enable(on: bool):
+    lib().kapre_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """(total kernel milliseconds, launches) recorded since the last read."""
+    ms, n = ctypes.c_double(0.0), c_uint64(0)
+    lib().kapre_profile_read(ctypes.byref(ms), ctypes.byref(n))
+    return float(ms.value), int(n.value)

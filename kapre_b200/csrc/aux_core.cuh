@@ -28,7 +28,7 @@ KB_HD KbFbSmem kb_fb_smem_layout(int F, int n_bands) {
     KbFbSmem s;
     s.Mp = n_bands | 1;
     s.mag = 0;
-    s.outs = kb_align16(F * 33 * 4);
+    s.outs = kb_align16((F + 3) * 33 * 4);
     s.total = s.outs + kb_align16(32 * s.Mp * 4);
     return s;
 }
@@ -61,6 +61,7 @@ __device__ __forceinline__ void kb_fb_cta(const KbFbParams& p, char* smem, int c
         KB_PHASE_BEGIN
             (void)R;
             const int tot = 32 * p.F;
+            for (int idx = tid; idx < 3 * 33; idx += kb_nt) mag_s[p.F * 33 + idx] = 0.0f;  // pad rows
             for (int idx = tid; idx < tot; idx += kb_nt) {
                 const int r = idx / p.F, k = idx - r * p.F;
                 const int t = t0 + r;
@@ -74,15 +75,8 @@ __device__ __forceinline__ void kb_fb_cta(const KbFbParams& p, char* smem, int c
             const float* mcol = mag_s + lane;
             for (int m = warp; m < p.n_bands; m += NW) {
                 const KbBand bd = p.bands[m];
-                const float* w = p.fbw + bd.off - bd.lo;
-                float a0 = 0.0f, a1 = 0.0f;
-                int k = bd.lo;
-                for (; k + 1 < bd.hi; k += 2) {
-                    a0 += kb_ldg(w + k) * mcol[k * 33];
-                    a1 += kb_ldg(w + k + 1) * mcol[(k + 1) * 33];
-                }
-                if (k < bd.hi) a0 += kb_ldg(w + k) * mcol[k * 33];
-                out_s[lane * L.Mp + m] = a0 + a1;
+                const float acc = kb_band_dot<33>(p.fbw + bd.off, mcol + bd.lo * 33, (bd.hi - bd.lo) >> 2);
+                out_s[lane * L.Mp + m] = acc;
             }
         KB_PHASE_END
         KB_SYNC_CTA;

@@ -26,6 +26,28 @@ static thread_local std::string g_err;
 static thread_local std::string g_launch_info;
 static std::atomic<uint64_t> g_launches{0};
 
+// optional kernel timing (bench.py roofline): event pairs around the dominant kernels
+#include <mutex>
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
+struct KbProfScope {
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    explicit KbProfScope(cudaStream_t s) : st(s) {
+        if (!g_prof_on) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, st);
+    }
+    ~KbProfScope() {
+        if (!e0) return;
+        cudaEventRecord(e1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_events.emplace_back(e0, e1);
+    }
+};
+
 static int kb_fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -46,14 +68,14 @@ static int kb_fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------
 // __global__ wrappers
 // ------------------------------------------------------------------------------------------
-template <int Q>
-__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_stft_kernel(const __grid_constant__ KbStftParams p) {
+template <int Q, int MODE>
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel(const __grid_constant__ KbStftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
-    kb_stft_cta<Q>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+    kb_stft_cta<Q, MODE>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
 template <int Q>
-__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_istft_kernel(const __grid_constant__ KbIstftParams p) {
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_istft_kernel(const __grid_constant__ KbIstftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
     kb_istft_cta<Q>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
@@ -172,10 +194,15 @@ struct kapre_istft_plan {
 };
 
 struct kapre_filterbank {
-    int n_freq, n_bands;
+    int n_freq, n_bands, n_w;
     DevInfo dev;
-    KbBand* bands = nullptr;
+    KbBand* bands = nullptr;   // band-major form (stand-alone ApplyFilterbank kernel)
     float* w = nullptr;
+    int Q = 0;                 // chunk-list form for the fused kernel (n_freq == 32*Q + 1), else 0
+    int n_chunks = 0;
+    kb_f4* cw = nullptr;
+    kb_i2* cm = nullptr;
+    int* cg = nullptr;
 };
 
 static int kb_env_int(const char* name, int dflt) {
@@ -188,23 +215,30 @@ static int kb_env_int(const char* name, int dflt) {
 // ------------------------------------------------------------------------------------------
 struct FwdCfg { int TF, NW, smem, bps; };
 
-static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int mode, int n_bands, FwdCfg* out) {
+// Tile shape of the fused forward kernel.  Measured on B200 (profiles/): the kernel is
+// latency-bound, so resident warps per SM (up to the 16 the 128-register kernel allows) matter
+// most, then larger tiles (less re-staging of the hop overlap).  Filterbank modes keep the
+// tile's magnitudes in the warps' exchange regions, which needs TF == frames per round.
+static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int mode, int n_bands, int n_chunks,
+                            FwdCfg* out) {
     const int FPW = 32 / Q;
+    const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     const int force_tf = kb_env_int("KAPRE_B200_TF", 0);
     const int force_nw = kb_env_int("KAPRE_B200_NW", 0);
     const int sm_smem = 228 * 1024;
     bool found = false;
     FwdCfg best{};
     long best_score = -1;
-    const int nws[2] = {4, 8};
-    for (int a = 0; a < 2; ++a) {
+    const int nws[3] = {2, 4, 8};
+    for (int a = 0; a < 3; ++a) {
         const int NW = nws[a];
         if (force_nw && NW != force_nw) continue;
+        const int FR = NW * FPW;
+        if (FR > 32) continue;
         for (int TF = 32; TF >= 1; TF >>= 1) {
-            if (force_tf && TF != force_tf) continue;
-            if (TF % FPW) continue;
-            if (!force_tf && TF < NW * FPW) continue;   // would leave warps without a frame
-            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands);
+            if (fb ? (TF != FR) : (TF % FR != 0)) continue;
+            if (!fb && force_tf && TF != force_tf) continue;
+            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands, n_chunks);
             if (L.total > dev.smem_optin) continue;
             int bps = sm_smem / (L.total + 1024);
             if (bps > 64 / NW) bps = 64 / NW;
@@ -212,7 +246,7 @@ static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int m
             if (bps < 1) continue;
             int warps = bps * NW;
             if (warps > 16) warps = 16;
-            const long score = (long)warps * 1000 + TF * 10 + (NW == 4 ? 1 : 0);
+            const long score = (long)warps * 1000 + TF * 10 + NW;
             if (score > best_score) {
                 best_score = score;
                 best = FwdCfg{TF, NW, L.total, bps};
@@ -231,20 +265,34 @@ static int kb_set_smem(K kernel, int smem) {
     return 0;
 }
 
-template <int Q>
-static int kb_launch_stft(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
-    int rc = kb_set_smem(kb_stft_kernel<Q>, smem);
+template <int Q, int MODE>
+static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    int rc = kb_set_smem(kb_stft_kernel<Q, MODE>, smem);
     if (rc) return rc;
-    kb_stft_kernel<Q><<<grid, p.n_warps * 32, smem, st>>>(p);
+    KbProfScope prof(st);
+    kb_stft_kernel<Q, MODE><<<grid, p.n_warps * 32, smem, st>>>(p);
     KB_CUDA(cudaGetLastError());
     g_launches++;
     return 0;
 }
 
 template <int Q>
+static int kb_launch_stft(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    switch (p.mode) {
+        case KB_OUT_COMPLEX: return kb_launch_stft_qm<Q, KB_OUT_COMPLEX>(p, grid, smem, st);
+        case KB_OUT_MAG: return kb_launch_stft_qm<Q, KB_OUT_MAG>(p, grid, smem, st);
+        case KB_OUT_MAG_DB: return kb_launch_stft_qm<Q, KB_OUT_MAG_DB>(p, grid, smem, st);
+        case KB_OUT_FB: return kb_launch_stft_qm<Q, KB_OUT_FB>(p, grid, smem, st);
+        case KB_OUT_FB_DB: return kb_launch_stft_qm<Q, KB_OUT_FB_DB>(p, grid, smem, st);
+    }
+    return kb_fail(KAPRE_E_INVALID, "bad mode");
+}
+
+template <int Q>
 static int kb_launch_istft(const KbIstftParams& p, int grid, int smem, cudaStream_t st) {
     int rc = kb_set_smem(kb_istft_kernel<Q>, smem);
     if (rc) return rc;
+    KbProfScope prof(st);
     kb_istft_kernel<Q><<<grid, p.n_warps * 32, smem, st>>>(p);
     KB_CUDA(cudaGetLastError());
     g_launches++;
@@ -298,6 +346,34 @@ const char* kapre_last_error(void) { return g_err.c_str(); }
 int kapre_version(void) { return KAPRE_B200_VERSION; }
 uint64_t kapre_launch_count(void) { return g_launches.load(); }
 const char* kapre_last_launch_info(void) { return g_launch_info.c_str(); }
+
+int kapre_profile_enable(int enable) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = enable != 0;
+    return 0;
+}
+
+int kapre_profile_read(double* total_ms, uint64_t* launches) {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        evs.swap(g_prof_events);
+    }
+    double tot = 0.0;
+    uint64_t n = 0;
+    for (auto& pr : evs) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            tot += ms;
+            ++n;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return 0;
+}
 
 int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const float* window_host,
                            kapre_stft_plan** out) {
@@ -376,6 +452,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         if (fb->n_freq != plan->n_fft / 2 + 1)
             return kb_fail(KAPRE_E_INVALID, "filterbank has %d rows but n_fft/2+1 = %d", fb->n_freq, plan->n_fft / 2 + 1);
         if (fb->dev.device != plan->dev.device) return kb_fail(KAPRE_E_INVALID, "filterbank lives on another device");
+        if (plan->Q && fb->Q != plan->Q) return kb_fail(KAPRE_E_INVALID, "filterbank was not prepared for n_fft=%d", plan->n_fft);
     }
     float db_mul = 0, db_sub = 0;
     if (dbmode) {
@@ -405,17 +482,27 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         return 0;
     }
 
+    // address range of the waveform tensor (non-negative strides): the rounded bulk copies stay inside
+    const long long max_off = (long long)(B - 1) * xd->stride_b + (long long)(C - 1) * xd->stride_c +
+                              (long long)(Ln - 1) * xd->stride_l;
+    const bool bulk = (xd->stride_l == 1) && (((uintptr_t)x_dev & 3) == 0) && xd->stride_b >= 0 && xd->stride_c >= 0 &&
+                      kb_env_int("KAPRE_B200_NOBULK", 0) == 0;
     FwdCfg cfg;
-    if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0, &cfg))
+    if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0,
+                         fbmode ? fb->n_chunks : 0, &cfg))
         return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
                        plan->n_fft, plan->hop, fbmode ? fb->n_bands : 0);
     KbStftParams p{};
     p.x = x_dev; p.x_sb = xd->stride_b; p.x_sc = xd->stride_c; p.x_sl = xd->stride_l;
     p.B = B; p.C = C; p.L = Ln; p.n_fft = plan->n_fft; p.hop = plan->hop; p.T = T; p.pad_left = pad_left;
+    p.x_lo = x_dev; p.x_hi = x_dev + max_off + 1; p.bulk_ok = bulk ? 1 : 0; p.dbuf = 0;
     p.wh = plan->wh; p.twp = plan->twp; p.twn = plan->twn;
     p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
     p.mode = mode;
-    if (fbmode) { p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands; }
+    if (fbmode) {
+        p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands; p.n_fbw = fb->n_w;
+        p.cw = fb->cw; p.cm = fb->cm; p.cg = fb->cg; p.n_chunks = fb->n_chunks;
+    }
     if (dbmode) { p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev; }
     p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
     const long long tiles = (long long)B * C * p.n_tiles_t;
@@ -433,7 +520,8 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if (rc) return rc;
     {
         char buf[160];
-        snprintf(buf, sizeof(buf), "Q%d TF%d NW%d grid%d smem%d bps%d tiles%lld", plan->Q, cfg.TF, cfg.NW, grid, cfg.smem, cfg.bps, tiles);
+        snprintf(buf, sizeof(buf), "Q%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld", plan->Q, cfg.TF, cfg.NW,
+                 (int)bulk, grid, cfg.smem, cfg.bps, tiles);
         g_launch_info = buf;
     }
     if (dbmode) {
@@ -568,14 +656,24 @@ int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre
     if (rc) { delete f; return rc; }
     std::vector<KbBand> bands; std::vector<float> w;
     kb_make_bands(fb_host, n_freq, n_bands, bands, w);
+    f->n_w = (int)w.size();
     if ((rc = kb_upload(bands, &f->bands)) || (rc = kb_upload(w, &f->w))) { kapre_filterbank_destroy(f); return rc; }
+    f->Q = kb_q_for_nfft((n_freq - 1) * 2);
+    if (f->Q) {
+        std::vector<kb_f4> cw; std::vector<kb_i2> cm; std::vector<int> cg;
+        kb_make_fb_chunks(fb_host, n_freq, n_bands, f->Q, cw, cm, cg);
+        f->n_chunks = (int)cw.size();
+        if ((rc = kb_upload(cw, &f->cw)) || (rc = kb_upload(cm, &f->cm)) || (rc = kb_upload(cg, &f->cg))) {
+            kapre_filterbank_destroy(f); return rc;
+        }
+    }
     *out = f;
     return 0;
 }
 
 void kapre_filterbank_destroy(kapre_filterbank* f) {
     if (!f) return;
-    cudaFree(f->bands); cudaFree(f->w);
+    cudaFree(f->bands); cudaFree(f->w); cudaFree(f->cw); cudaFree(f->cm); cudaFree(f->cg);
     delete f;
 }
 

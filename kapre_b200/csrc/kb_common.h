@@ -22,6 +22,9 @@ static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b;
 
 #define KB_MAX_WARPS 8
 
+struct alignas(16) kb_f4 { float x, y, z, w; };
+struct alignas(8) kb_i2 { int x, y; };
+
 // ---- output modes of the fused forward kernel -------------------------------------------
 enum KbMode {
     KB_OUT_COMPLEX = 0,  // complex64 STFT            (kapre.STFT)
@@ -31,7 +34,8 @@ enum KbMode {
     KB_OUT_FB_DB = 4,    // dB(filterbank(|STFT|))    (get_melspectrogram_layer(return_decibel))
 };
 
-// Filterbank in "banded" form: band m covers bins [lo, hi) with weights w[off + (k - lo)].
+// Filterbank in "banded" form: band m covers bins [lo, hi) with weights w[off + (k - lo)];
+// off and hi - lo are multiples of 4 (zero-padded) so the kernels read weights as 16 B vectors.
 struct KbBand { int lo, hi, off, pad; };
 
 struct KbStftParams {
@@ -39,6 +43,12 @@ struct KbStftParams {
     const float* x;
     long long x_sb, x_sc, x_sl;
     int B, C, L;
+    // [x_lo, x_hi): byte range of the waveform tensor; the 16 B-rounded TMA bulk copies must
+    // stay inside it.  bulk_ok: x_sl == 1 and x is 4 B-aligned (else the fallback loader runs).
+    const void* x_lo;
+    const void* x_hi;
+    int bulk_ok;
+    int dbuf;            // 1: two sample buffers (next tile prefetched during the current one)
     // transform
     int n_fft, hop, T;   // T = number of frames per (batch, channel)
     int pad_left;        // zeros prepended (n_fft - hop if pad_begin)  kapre/time_frequency.py:169-172
@@ -55,6 +65,14 @@ struct KbStftParams {
     const KbBand* bands;
     const float* fbw;
     int n_bands;
+    int n_fbw;           // floats in fbw (bands are padded to multiples of 4 weights)
+    // the same filterbank as flat lists of 4-weight chunks, one list per lane group (Q groups):
+    // chunk i multiplies bins [cm[i].x, cm[i].x + 4); cm[i].y is the band to store after this
+    // chunk (its last one) or -1.  Group g owns chunks [cg[g], cg[g+1]).
+    const kb_f4* cw;
+    const kb_i2* cm;
+    const int* cg;
+    int n_chunks;
     // decibel (modes *_DB): y = db_mul * log2(max(v, amin)) - db_sub; per-item max of max(v, amin)
     float amin, db_mul, db_sub;
     unsigned int* item_max;  // B entries, uint view of non-negative floats, zero-initialised

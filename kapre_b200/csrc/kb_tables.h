@@ -49,7 +49,9 @@ static inline void kb_make_wh(const float* window, int win_length, int n_fft, st
 }
 
 // Banded form of a (n_freq x n_bands) row-major filterbank: per band the tight support
-// [lo, hi) of its non-zero weights (interior zeros kept).
+// [lo, hi) of its non-zero weights (interior zeros kept), zero-padded so that both the offset
+// into the weight array and hi - lo are multiples of 4 (hi may exceed n_freq by up to 3: the
+// kernels keep three zero rows behind the magnitudes).
 static inline void kb_make_bands(const float* fb, int n_freq, int n_bands,
                                  std::vector<KbBand>& bands, std::vector<float>& w) {
     bands.resize(n_bands);
@@ -62,12 +64,47 @@ static inline void kb_make_bands(const float* fb, int n_freq, int n_bands,
                 hi = k + 1;
             }
         if (hi <= lo) { lo = 0; hi = 0; }
+        const int len4 = (hi - lo + 3) & ~3;
         KbBand b;
-        b.lo = lo; b.hi = hi; b.off = (int)w.size(); b.pad = 0;
-        for (int k = lo; k < hi; ++k) w.push_back(fb[(size_t)k * n_bands + m]);
+        b.lo = lo; b.hi = lo + len4; b.off = (int)w.size(); b.pad = 0;
+        for (int k = lo; k < lo + len4; ++k) w.push_back(k < hi ? fb[(size_t)k * n_bands + m] : 0.0f);
         bands[m] = b;
     }
-    if (w.empty()) w.push_back(0.0f);
+    if (w.empty()) w.assign(4, 0.0f);
+}
+
+// Chunk-list form for the fused kernel's filterbank phase: bands are dealt round-robin to
+// `groups` lane groups (band m -> group m % groups); each band becomes ceil(len/4) chunks of 4
+// consecutive bins.  An all-zero band still gets one (zero) chunk so that its output is written.
+static inline void kb_make_fb_chunks(const float* fb, int n_freq, int n_bands, int groups,
+                                     std::vector<kb_f4>& cw, std::vector<kb_i2>& cm, std::vector<int>& cg) {
+    cw.clear(); cm.clear(); cg.assign(groups + 1, 0);
+    for (int g = 0; g < groups; ++g) {
+        cg[g] = (int)cw.size();
+        for (int m = g; m < n_bands; m += groups) {
+            int lo = n_freq, hi = 0;
+            for (int k = 0; k < n_freq; ++k)
+                if (fb[(size_t)k * n_bands + m] != 0.0f) {
+                    if (k < lo) lo = k;
+                    hi = k + 1;
+                }
+            if (hi <= lo) { lo = 0; hi = 1; }
+            for (int k0 = lo; k0 < hi; k0 += 4) {
+                kb_f4 w;
+                float* wp = &w.x;
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + j;
+                    wp[j] = (k < hi && k < n_freq) ? fb[(size_t)k * n_bands + m] : 0.0f;
+                }
+                kb_i2 mt;
+                mt.x = k0;
+                mt.y = (k0 + 4 >= hi) ? m : -1;
+                cw.push_back(w);
+                cm.push_back(mt);
+            }
+        }
+    }
+    cg[groups] = (int)cw.size();
 }
 
 // Synthesis-window table for the inverse kernel: dual[m] = w~[m] / n_fft, negated for odd m

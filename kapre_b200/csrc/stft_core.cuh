@@ -8,6 +8,13 @@
 // The per-item clamp of kapre/backend.py:190-192 needs the item-wide maximum, so this
 // kernel only reduces that maximum (atomicMax) and a second tiny kernel applies the clamp.
 //
+// Data movement: a persistent CTA walks tiles of TF consecutive frames of one (batch,
+// channel) signal.  The hop-overlapped sample span of the NEXT tile is fetched with one TMA
+// bulk copy (cp.async.bulk + mbarrier) into the other half of a double buffer while the
+// current tile is transformed, so every sample is read from HBM/L2 once per tile and the
+// load latency is off the critical path.  Strided (interleaved-channel) inputs use a
+// cooperative fallback loader.
+//
 // Real FFT of length N as one complex FFT of length P = N/2 = 32*Q on the packed signal
 // z[n] = x[2n] + i x[2n+1]; Q lanes of a warp cooperate on one frame (32/Q frames per warp):
 //   pass 1  lane q: 32-point DFT over j of z[q + Q j]        (registers)
@@ -15,33 +22,46 @@
 //   pass 2  lane q: Q-point DFTs over the columns k1 = q + Q i (registers)
 //           Z[k1 + 32 k2] written back in natural order
 //   pair    X[k], X[P-k] from Z[k], Z[P-k] and exp(-2 pi i k / N)  -> output epilogue
+// Filterbank epilogue: magnitudes of the tile stay in shared memory ([bin][frame]); one lane
+// per frame column accumulates a band with warp-uniform weights (vector loads from smem).
 #pragma once
 #include "fft_regs.cuh"
 
 struct KbStftSmem {
-    int wh, twp, twn, samples, ex, mag, total;  // byte offsets
-    int span;   // samples staged per tile
-    int TFp;    // padded column stride of mag_s
-    int Mp;     // padded band stride of out_s
+    int wh, twp, twn, cw, cm, cg, bar, samples, outs, ex, total;  // byte offsets
+    int span;       // samples staged per tile
+    int exw;        // complex elements per warp in the exchange buffer (incl. bank skew)
+    int Mp;         // padded band stride of out_s
 };
 
+// Per-warp exchange region: 32 x 33 complex for the FFT transpose, plus a skew so that the
+// magnitudes the filterbank phase reads from all warps' regions ([bin][frame-in-warp]) land in
+// distinct banks for distinct frame columns.
+KB_HD int kb_exw(int Q) {
+    const int FPW = 32 / Q;
+    return 32 * 33 + (FPW >= 2 ? FPW / 2 : 1);
+}
+
 // Shared-memory carve-up; used by the host launcher (size) and by the kernel (offsets).
-KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_warps, int mode, int n_bands) {
+KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_warps, int mode,
+                                     int n_bands, int n_chunks) {
     KbStftSmem s;
     const int P = 32 * Q;
+    const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     int off = 0;
     s.wh = off;  off += kb_align16(n_fft * 4);
     s.twp = off; off += kb_align16(Q * 33 * 8);
     s.twn = off; off += kb_align16((P / 2) * 8);
+    s.cw = off; if (fb) off += n_chunks * 16;
+    s.cm = off; if (fb) off += kb_align16(n_chunks * 8);
+    s.cg = off; if (fb) off += kb_align16((Q + 1) * 4);
+    s.bar = off; off += 16;
     s.span = (TF - 1) * hop + n_fft;
-    s.TFp = TF | 1;
     s.Mp = n_bands | 1;
-    int samp_floats = s.span + 2;
-    const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
-    if (fb && TF * s.Mp > samp_floats) samp_floats = TF * s.Mp;  // out_s aliases the sample buffer
-    s.samples = off; off += kb_align16(samp_floats * 4);
-    s.ex = off;  off += n_warps * (32 * 33 * 8);
-    s.mag = off; if (fb) off += kb_align16((P + 1) * s.TFp * 4);
+    s.samples = off; off += kb_align16((s.span + 8) * 4);  // +4 front (alignment shift) +4 back (rounded copy)
+    s.outs = off; if (fb) off += kb_align16(TF * s.Mp * 4);
+    s.exw = kb_exw(Q);
+    s.ex = off;  off += kb_align16(n_warps * s.exw * 8);
     s.total = off;
     return s;
 }
@@ -63,6 +83,11 @@ static inline float kb_log2(float v) { return std::log2(v); }
 static inline float kb_ldg(const float* p) { return *p; }
 static inline void kb_atomic_max_u32(unsigned int* p, unsigned int v) { if (v > *p) *p = v; }
 static inline unsigned int kb_f2u(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
+// async staging primitives: the emulation copies synchronously and barriers are no-ops
+typedef unsigned long long KbBar;
+static inline void kb_bar_init(KbBar*, int) {}
+static inline void kb_bulk_g2s(void* dst, const void* src, int bytes, KbBar*) { std::memcpy(dst, src, bytes); }
+static inline void kb_bar_wait(KbBar*, unsigned) {}
 #else
 #define KB_PHASE_BEGIN { const int tid = threadIdx.x; KbThreadRegs& R = kb_regs;
 #define KB_PHASE_END }
@@ -73,11 +98,148 @@ KB_D float kb_log2(float v) { return __log2f(v); }
 KB_D float kb_ldg(const float* p) { return __ldg(p); }
 KB_D void kb_atomic_max_u32(unsigned int* p, unsigned int v) { atomicMax(p, v); }
 KB_D unsigned int kb_f2u(float f) { return __float_as_uint(f); }
+typedef unsigned long long KbBar;
+KB_D unsigned int kb_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+KB_D void kb_bar_init(KbBar* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kb_smem_u32(b)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// One TMA bulk copy global -> shared (SASS: UBLKCP), completion signalled on the mbarrier.
+KB_D void kb_bulk_g2s(void* dst, const void* src, int bytes, KbBar* bar) {
+    const unsigned int b = kb_smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(kb_smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+KB_D void kb_bar_wait(KbBar* bar, unsigned parity) {
+    const unsigned int b = kb_smem_u32(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KB_DONE_%=;\n\t"
+        "bra KB_WAIT_%=;\n\t"
+        "KB_DONE_%=:\n\t}"
+        ::"r"(b), "r"(parity) : "memory");
+}
 #endif
 
-// One CTA's share of the work: tiles cta, cta + n_cta, ... ; a tile is TF consecutive frames
-// of one (batch, channel) signal.
-template <int Q>
+// Where a tile's samples come from.  Everything here is a pure function of the tile index,
+// so every thread computes the same plan (no broadcast needed).
+struct KbTilePlan {
+    int b, c, t0;
+    long long s_first;   // first padded-signal sample of the tile (may be negative: pad_begin)
+    int v0, v1;          // valid (non-pad) range in tile coordinates [v0, v1), v0 == v1: all pad
+    int shift;           // smem index of tile sample i is i + shift
+    int bulk;            // 1: one TMA bulk copy, 0: cooperative loads
+    const float* src;    // 16 B-aligned source of the bulk copy
+    int dst;             // smem float index (multiple of 4) of the bulk copy
+    int bytes;           // multiple of 16
+};
+
+KB_HD KbTilePlan kb_plan_tile(const KbStftParams& p, int span, int tile) {
+    KbTilePlan t;
+    const int sig = tile / p.n_tiles_t;
+    const int tt = tile - sig * p.n_tiles_t;
+    t.b = sig / p.C;
+    t.c = sig - t.b * p.C;
+    t.t0 = tt * p.TF;
+    t.s_first = (long long)t.t0 * p.hop - p.pad_left;
+    long long a = -t.s_first, e = (long long)p.L - t.s_first;
+    if (a < 0) a = 0;
+    if (e > span) e = span;
+    if (e < a) e = a;
+    t.v0 = (int)a; t.v1 = (int)e;
+    t.shift = 0; t.bulk = 0; t.src = nullptr; t.dst = 0; t.bytes = 0;
+    if (p.x_sl == 1 && p.bulk_ok && t.v1 > t.v0) {
+        const float* xsig = p.x + (long long)t.b * p.x_sb + (long long)t.c * p.x_sc;
+        const float* g0 = xsig + (t.s_first + t.v0);            // first valid sample
+        const float* g1 = xsig + (t.s_first + t.v1);            // one past the last valid sample
+        const uintptr_t a0 = (uintptr_t)g0 & ~(uintptr_t)15;
+        const uintptr_t a1 = ((uintptr_t)g1 + 15) & ~(uintptr_t)15;
+        if (a0 >= (uintptr_t)p.x_lo && a1 <= (uintptr_t)p.x_hi) {
+            const int head = (int)(((uintptr_t)g0 - a0) >> 2);  // 0..3 floats fetched before v0
+            t.shift = (head - t.v0) & 3;                        // makes (v0 + shift - head) % 4 == 0
+            t.bulk = 1;
+            t.src = reinterpret_cast<const float*>(a0);
+            t.dst = t.v0 + t.shift - head;
+            t.bytes = (int)(a1 - a0);
+            if (t.dst < 0) { t.shift += 4; t.dst += 4; }
+        }
+    }
+    return t;
+}
+
+// Issue the loads of one tile into sample buffer `buf` (all threads call this).
+// Pad regions are zero-filled with plain stores; the <= 3 floats on either side of the valid
+// range that the 16 B-rounded bulk copy may overwrite are re-zeroed by kb_finish_tile_loads.
+#if defined(KB_HOST_EMU)
+inline void kb_issue_tile_loads(const KbStftParams& p, const KbTilePlan& t, float* buf, int span, KbBar* bar,
+                                int tid, int nt)
+#else
+__device__ __forceinline__ void kb_issue_tile_loads(const KbStftParams& p, const KbTilePlan& t, float* buf,
+                                                    int span, KbBar* bar, int tid, int nt)
+#endif
+{
+    float* s = buf + t.shift;
+    if (t.bulk) {
+        if (tid == 0) kb_bulk_g2s(buf + t.dst, t.src, t.bytes, bar);
+        for (int i = tid; i < t.v0 - 4; i += nt) s[i] = 0.0f;
+        for (int i = t.v1 + 4 + tid; i < span; i += nt) s[i] = 0.0f;
+    } else {
+        const float* xsig = p.x + (long long)t.b * p.x_sb + (long long)t.c * p.x_sc + t.s_first * p.x_sl;
+        int i = tid;
+        for (; i + 3 * nt < span; i += 4 * nt) {   // 4 independent loads in flight per thread
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ii = i + u * nt;
+                v[u] = (ii >= t.v0 && ii < t.v1) ? xsig[(long long)ii * p.x_sl] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[i + u * nt] = v[u];
+        }
+        for (; i < span; i += nt) s[i] = (i >= t.v0 && i < t.v1) ? xsig[(long long)i * p.x_sl] : 0.0f;
+    }
+}
+
+// After the bulk copy has landed: restore the zeros next to the valid range.  Returns
+// whether anything was (possibly) written, i.e. whether a CTA barrier is needed.
+#if defined(KB_HOST_EMU)
+inline bool kb_finish_tile_loads(const KbTilePlan& t, float* buf, int span, int tid)
+#else
+__device__ __forceinline__ bool kb_finish_tile_loads(const KbTilePlan& t, float* buf, int span, int tid)
+#endif
+{
+    if (!t.bulk) return false;
+    const bool edge = (t.v0 > 0) || (t.v1 < span);
+    if (edge && tid < 8) {
+        float* s = buf + t.shift;
+        const int i = (tid < 4) ? (t.v0 - 1 - tid) : (t.v1 + (tid - 4));
+        if (i >= 0 && i < span && (i < t.v0 || i >= t.v1)) s[i] = 0.0f;
+    }
+    return edge;
+}
+
+// Filterbank accumulation for one band: warp-uniform weights (16 B vectors from smem), one
+// frame column per lane; `mc` points at the column's magnitude for bin lo, consecutive bins are
+// FPW floats apart ([bin][frame-in-warp] layout inside the owning warp's exchange region).
+template <int FPW>
+KB_HD float kb_band_dot(const float* __restrict__ w, const float* __restrict__ mc, int len4) {
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    for (int i = 0; i < len4; ++i) {
+        const kb_f4 wv = reinterpret_cast<const kb_f4*>(w)[i];   // 16 B, warp-uniform address
+        a0 += wv.x * mc[0];
+        a1 += wv.y * mc[FPW];
+        a2 += wv.z * mc[2 * FPW];
+        a3 += wv.w * mc[3 * FPW];
+        mc += 4 * FPW;
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+// One CTA's share of the work: tiles cta, cta + n_cta, ...
+template <int Q, int MODE>
 #if defined(KB_HOST_EMU)
 inline void kb_stft_cta(const KbStftParams& p, char* smem, int cta, int n_cta)
 #else
@@ -88,23 +250,28 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     constexpr int FPW = 32 / Q;      // frames per warp per round
     constexpr int ZSTR = P + Q;      // frame stride (complex) of the natural-order buffer
     constexpr int EXW = 32 * 33;     // complex elements per warp in the exchange buffer
+    constexpr bool fbmode = (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB);
+    constexpr bool dbmode = (MODE == KB_OUT_MAG_DB || MODE == KB_OUT_FB_DB);
     const int NW = p.n_warps;
     const int kb_nt = NW * 32;
     (void)kb_nt;
     const int H = p.hop, N = p.n_fft, TF = p.TF;
-    const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, p.mode, p.n_bands);
-    float* wh_s = reinterpret_cast<float*>(smem + L.wh);
-    cpx* twp_s = reinterpret_cast<cpx*>(smem + L.twp);
-    cpx* twn_s = reinterpret_cast<cpx*>(smem + L.twn);
-    float* smp_s = reinterpret_cast<float*>(smem + L.samples);
+    const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, p.n_chunks);
+    float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
+    cpx* __restrict__ twp_s = reinterpret_cast<cpx*>(smem + L.twp);
+    cpx* __restrict__ twn_s = reinterpret_cast<cpx*>(smem + L.twn);
+    kb_f4* __restrict__ cw_s = reinterpret_cast<kb_f4*>(smem + L.cw);
+    kb_i2* __restrict__ cm_s = reinterpret_cast<kb_i2*>(smem + L.cm);
+    int* __restrict__ cg_s = reinterpret_cast<int*>(smem + L.cg);
+    KbBar* bar = reinterpret_cast<KbBar*>(smem + L.bar);
+    float* smp0 = reinterpret_cast<float*>(smem + L.samples);
+    float* __restrict__ out_s = reinterpret_cast<float*>(smem + L.outs);
     cpx* ex_s = reinterpret_cast<cpx*>(smem + L.ex);
-    float* mag_s = reinterpret_cast<float*>(smem + L.mag);
-    float* out_s = smp_s;  // aliases the sample buffer (dead once the FFT rounds are done)
-    const bool fbmode = (p.mode == KB_OUT_FB || p.mode == KB_OUT_FB_DB);
-    const bool dbmode = (p.mode == KB_OUT_MAG_DB || p.mode == KB_OUT_FB_DB);
+    const int EXS = L.exw;                         // per-warp stride (complex) incl. bank skew
     const int FR = NW * FPW;                       // frames per round
-    const int n_rounds = (TF + FR - 1) / FR;
+    const int n_rounds = fbmode ? 1 : (TF + FR - 1) / FR;   // filterbank modes: TF == FR (host guarantees)
     const int n_tiles = p.B * p.C * p.n_tiles_t;
+    const int span = L.span;
 
 #if defined(KB_HOST_EMU)
     std::vector<KbThreadRegs> kb_regs(kb_nt);
@@ -112,35 +279,51 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     KbThreadRegs kb_regs;
 #endif
 
-    // ---- one-time: tables to shared memory -------------------------------------------------
+    // ---- one-time: tables to shared memory, barrier, first tile's loads ----------------------
     KB_PHASE_BEGIN
         (void)R;
+        if (tid == 0) kb_bar_init(bar, 1);
         for (int i = tid; i < N; i += kb_nt) wh_s[i] = p.wh[i];
         for (int i = tid; i < Q * 33; i += kb_nt) { float2 t = p.twp[i]; twp_s[i] = cmake(t.x, t.y); }
         for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
+        if (fbmode) {
+            for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
+            for (int i = tid; i <= Q; i += kb_nt) cg_s[i] = p.cg[i];
+        }
     KB_PHASE_END
     KB_SYNC_CTA;
+    unsigned par = 0;   // mbarrier phase parity (uniform across the CTA)
+    if (cta < n_tiles) {
+        const KbTilePlan tp = kb_plan_tile(p, span, cta);
+        KB_PHASE_BEGIN
+            (void)R;
+            kb_issue_tile_loads(p, tp, smp0, span, bar, tid, kb_nt);
+        KB_PHASE_END
+    }
 
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
-        const int sig = tile / p.n_tiles_t;
-        const int tt = tile - sig * p.n_tiles_t;
-        const int b = sig / p.C, c = sig - b * p.C;
-        const int t0 = tt * TF;
-        const float* xsig = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc;
+        const KbTilePlan tp = kb_plan_tile(p, span, tile);
+        const int b = tp.b, c = tp.c, t0 = tp.t0;
         const long long obase = (long long)b * p.o_sb + (long long)c * p.o_sc;
+        const float* __restrict__ smp_s = smp0 + tp.shift;
+        const bool has_next = (tile + n_cta) < n_tiles;
 
-        // ---- phase 0: stage the tile's samples (zero outside [0, L): pad_begin / pad_end) ----
-        KB_PHASE_BEGIN
-            R.runmax = 0.0f;
-            const long long s_first = (long long)t0 * H - p.pad_left;
-            for (int i = tid; i < L.span; i += kb_nt) {
-                const long long s = s_first + i;
-                float val = 0.0f;
-                if (s >= 0 && s < p.L) val = xsig[s * p.x_sl];
-                smp_s[i] = val;
-            }
-        KB_PHASE_END
-        KB_SYNC_CTA;
+        // ---- wait for this tile's samples -----------------------------------------------------
+        if (tp.bulk) {
+#if !defined(KB_HOST_EMU)
+            kb_bar_wait(bar, par);
+#endif
+            par ^= 1u;
+        }
+        {
+            bool need = false;
+            KB_PHASE_BEGIN
+                R.runmax = 0.0f;
+                need = kb_finish_tile_loads(tp, smp0, span, tid);
+            KB_PHASE_END
+            if (need || !tp.bulk) { KB_SYNC_CTA; }
+        }
+        const bool even_base = (((tp.shift & 1) == 0) && ((H & 1) == 0));
 
         for (int round = 0; round < n_rounds; ++round) {
             // ---- phase 1: window, 32-point DFTs, twiddle, transpose-store ------------------
@@ -150,7 +333,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int col = round * FR + warp * FPW + g;
                 if (col < TF) {
                     const float* fr = smp_s + col * H;
-                    if ((H & 1) == 0) {
+                    if (even_base) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n2 = 2 * (q + Q * j);
@@ -166,21 +349,33 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                         }
                     }
                     kb_fft_dif<32>(R.v);
-                    cpx* ex = ex_s + warp * EXW + (g * Q + q) * 33;
+                    cpx* ex = ex_s + warp * EXS + (g * Q + q) * 33;
                     const cpx* tw = twp_s + q * 33;
                     ex[0] = R.v[0];
 #pragma unroll
                     for (int k1 = 1; k1 < 32; ++k1) ex[k1] = cmul(R.v[kb_brev<32>(k1)], tw[k1]);
                 }
             KB_PHASE_END
-            KB_SYNC_WARP;
+            if (round == n_rounds - 1 && !fbmode) {
+                // every warp has consumed the sample buffer: fetch the next tile behind phases 2-4
+                KB_SYNC_CTA;
+                if (has_next) {
+                    const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
+                    KB_PHASE_BEGIN
+                        (void)R;
+                        kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
+                    KB_PHASE_END
+                }
+            } else {
+                KB_SYNC_WARP;
+            }
             // ---- phase 2: gather this lane's columns --------------------------------------
             KB_PHASE_BEGIN
                 const int warp = tid >> 5, lane = tid & 31;
                 const int g = lane / Q, q = lane % Q;
                 const int col = round * FR + warp * FPW + g;
                 if (col < TF) {
-                    const cpx* ex = ex_s + warp * EXW + (g * Q) * 33;
+                    const cpx* ex = ex_s + warp * EXS + (g * Q) * 33;
 #pragma unroll
                     for (int i = 0; i < FPW; ++i) {
                         const int k1 = q + Q * i;
@@ -196,7 +391,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int g = lane / Q, q = lane % Q;
                 const int col = round * FR + warp * FPW + g;
                 if (col < TF) {
-                    cpx* zs = ex_s + warp * EXW + g * ZSTR;
+                    cpx* zs = ex_s + warp * EXS + g * ZSTR;
 #pragma unroll
                     for (int i = 0; i < FPW; ++i) {
                         kb_fft_dif<Q>(R.v + i * Q);
@@ -208,16 +403,22 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
             KB_PHASE_END
             KB_SYNC_WARP;
             // ---- phase 4: real-FFT pair post-processing + epilogue -------------------------
+            // Filterbank modes park the magnitudes in registers (R.v is dead) and store them in
+            // phase 4b, because they overwrite the warp's natural-order buffer in place.
             KB_PHASE_BEGIN
                 const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll 1
+                float* magr = reinterpret_cast<float*>(R.v);
+#pragma unroll
                 for (int gg = 0; gg < FPW; ++gg) {
                     const int col = round * FR + warp * FPW + gg;
                     const int t = t0 + col;
                     if (col >= TF) break;
                     const bool valid = t < p.T;
-                    const cpx* zf = ex_s + warp * EXW + gg * ZSTR;
+                    const cpx* zf = ex_s + warp * EXS + gg * ZSTR;
                     const long long ofr = obase + (long long)t * p.o_st;
+                    const int sk = (int)p.o_sk;
+                    float2* oc = reinterpret_cast<float2*>(p.out) + ofr;
+                    float* orl = reinterpret_cast<float*>(p.out) + ofr;
 #pragma unroll
                     for (int i = 0; i <= Q / 2; ++i) {
                         cpx X1, X2;
@@ -234,39 +435,45 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                             const float Ti = W.im * Di - W.re * Dr;
                             X1 = cmake(Er + Tr, Ei + Ti);
                             X2 = cmake(Er - Tr, Ti - Ei);
-                        } else {  // bin P/2 pairs with itself; lane 0 only
-                            if (lane != 0) continue;
+                        } else {  // bin P/2 pairs with itself; only lane 0's value is used
                             k = P / 2;
                             kk = -1;
                             const cpx A = zf[P / 2];
                             X1 = cmake(2.0f * A.re, -2.0f * A.im);
                             X2 = X1;
+                            if (!fbmode && lane != 0) continue;
                         }
-                        if (p.mode == KB_OUT_COMPLEX) {
+                        if (MODE == KB_OUT_COMPLEX) {
                             if (valid) {
-                                float2* o = reinterpret_cast<float2*>(p.out);
-                                o[ofr + (long long)k * p.o_sk] = make_float2(X1.re, X1.im);
-                                if (kk >= 0) o[ofr + (long long)kk * p.o_sk] = make_float2(X2.re, X2.im);
+                                if (sk == 1) {
+                                    oc[k] = make_float2(X1.re, X1.im);
+                                    if (kk >= 0) oc[kk] = make_float2(X2.re, X2.im);
+                                } else {
+                                    oc[k * sk] = make_float2(X1.re, X1.im);
+                                    if (kk >= 0) oc[kk * sk] = make_float2(X2.re, X2.im);
+                                }
                             }
                         } else {
-                            const float m1 = kb_sqrt(X1.re * X1.re + X1.im * X1.im);
-                            const float m2 = kb_sqrt(X2.re * X2.re + X2.im * X2.im);
+                            float m1 = kb_sqrt(X1.re * X1.re + X1.im * X1.im);
+                            float m2 = kb_sqrt(X2.re * X2.re + X2.im * X2.im);
                             if (fbmode) {
-                                mag_s[k * L.TFp + col] = m1;
-                                if (kk >= 0) mag_s[kk * L.TFp + col] = m2;
+                                magr[(gg * (Q / 2 + 1) + i) * 2 + 0] = m1;
+                                magr[(gg * (Q / 2 + 1) + i) * 2 + 1] = m2;
                             } else if (valid) {
-                                float* o = reinterpret_cast<float*>(p.out);
                                 if (dbmode) {
-                                    const float a1 = fmaxf(m1, p.amin), a2 = fmaxf(m2, p.amin);
-                                    R.runmax = fmaxf(R.runmax, a1);
-                                    o[ofr + (long long)k * p.o_sk] = p.db_mul * kb_log2(a1) - p.db_sub;
-                                    if (kk >= 0) {
-                                        R.runmax = fmaxf(R.runmax, a2);
-                                        o[ofr + (long long)kk * p.o_sk] = p.db_mul * kb_log2(a2) - p.db_sub;
-                                    }
+                                    m1 = fmaxf(m1, p.amin);
+                                    m2 = fmaxf(m2, p.amin);
+                                    R.runmax = fmaxf(R.runmax, m1);
+                                    if (kk >= 0) R.runmax = fmaxf(R.runmax, m2);
+                                    m1 = p.db_mul * kb_log2(m1) - p.db_sub;
+                                    m2 = p.db_mul * kb_log2(m2) - p.db_sub;
+                                }
+                                if (sk == 1) {
+                                    orl[k] = m1;
+                                    if (kk >= 0) orl[kk] = m2;
                                 } else {
-                                    o[ofr + (long long)k * p.o_sk] = m1;
-                                    if (kk >= 0) o[ofr + (long long)kk * p.o_sk] = m2;
+                                    orl[k * sk] = m1;
+                                    if (kk >= 0) orl[kk * sk] = m2;
                                 }
                             }
                         }
@@ -274,48 +481,86 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 }
             KB_PHASE_END
             KB_SYNC_WARP;
+            if (fbmode) {
+                // ---- phase 4b: magnitudes -> own exchange region, layout [bin][frame-in-warp] ---
+                KB_PHASE_BEGIN
+                    const int warp = tid >> 5, lane = tid & 31;
+                    const float* magr = reinterpret_cast<const float*>(R.v);
+                    float* mw = reinterpret_cast<float*>(ex_s + warp * EXS);
+#pragma unroll
+                    for (int gg = 0; gg < FPW; ++gg) {
+#pragma unroll
+                        for (int i = 0; i < Q / 2; ++i) {
+                            const int k = lane + 32 * i;
+                            mw[k * FPW + gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 0];
+                            mw[(P - k) * FPW + gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 1];
+                        }
+                        if (lane == 0) mw[(P / 2) * FPW + gg] = magr[(gg * (Q / 2 + 1) + Q / 2) * 2 + 0];
+                        if (lane < 3) mw[(P + 1 + lane) * FPW + gg] = 0.0f;   // pad bins read by padded bands
+                    }
+                KB_PHASE_END
+            }
         }  // rounds
 
         if (fbmode) {
-            KB_SYNC_CTA;
+            KB_SYNC_CTA;   // all magnitudes visible; sample buffer and out_s are free
+            if (has_next) {
+                const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
+                KB_PHASE_BEGIN
+                    (void)R;
+                    kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
+                KB_PHASE_END
+            }
             // ---- phase 5: filterbank, one lane per frame column (uniform weights) ----------
             KB_PHASE_BEGIN
+                (void)R;
                 const int warp = tid >> 5, lane = tid & 31;
                 const int cpw = TF < 32 ? TF : 32;     // columns per warp
                 const int subs = 32 / cpw;             // band sub-groups per warp
                 const int colm = lane % cpw, sub = lane / cpw;
-                const bool valid = (t0 + colm) < p.T;
-                const float* mcol = mag_s + colm;
-                for (int m = warp * subs + sub; m < p.n_bands; m += NW * subs) {
-                    const KbBand bd = p.bands[m];
-                    const float* w = p.fbw + bd.off - bd.lo;
+                const float* __restrict__ mcol = reinterpret_cast<const float*>(ex_s + (colm / FPW) * EXS) + (colm % FPW);
+                float* __restrict__ orow_s = out_s + colm * L.Mp;
+                const int grp = warp * subs + sub;          // lane group: Q of them per CTA
+                if (grp < Q) {
+                    const int ce = cg_s[grp + 1];
                     float a0 = 0.0f, a1 = 0.0f;
-                    int k = bd.lo;
-                    for (; k + 1 < bd.hi; k += 2) {
-                        a0 += kb_ldg(w + k) * mcol[k * L.TFp];
-                        a1 += kb_ldg(w + k + 1) * mcol[(k + 1) * L.TFp];
+                    for (int i = cg_s[grp]; i < ce; ++i) {
+                        const kb_f4 w = cw_s[i];            // 16 B, uniform within the lane group
+                        const kb_i2 mt = cm_s[i];
+                        const float* mc = mcol + mt.x * FPW;
+                        a0 += w.x * mc[0];
+                        a1 += w.y * mc[FPW];
+                        a0 += w.z * mc[2 * FPW];
+                        a1 += w.w * mc[3 * FPW];
+                        if (mt.y >= 0) {
+                            orow_s[mt.y] = a0 + a1;
+                            a0 = 0.0f;
+                            a1 = 0.0f;
+                        }
                     }
-                    if (k < bd.hi) a0 += kb_ldg(w + k) * mcol[k * L.TFp];
-                    float acc = a0 + a1;
-                    if (dbmode) {
-                        acc = fmaxf(acc, p.amin);
-                        if (valid) R.runmax = fmaxf(R.runmax, acc);
-                        acc = p.db_mul * kb_log2(acc) - p.db_sub;
-                    }
-                    out_s[colm * L.Mp + m] = acc;
                 }
             KB_PHASE_END
             KB_SYNC_CTA;
-            // ---- phase 6: coalesced copy-out of the (TF x n_bands) block --------------------
+            // ---- phase 6: decibel + coalesced copy-out of the (TF x n_bands) block ----------
             KB_PHASE_BEGIN
-                (void)R;
-                float* o = reinterpret_cast<float*>(p.out);
+                const int warp = tid >> 5, lane = tid & 31;
+                float* o = reinterpret_cast<float*>(p.out) + obase;
                 const int M = p.n_bands;
-                const int tot = TF * M;
-                for (int idx = tid; idx < tot; idx += kb_nt) {
-                    const int colm = idx / M, m = idx - colm * M;
+                const int sk = (int)p.o_sk;
+                for (int colm = warp; colm < TF; colm += NW) {
                     const int t = t0 + colm;
-                    if (t < p.T) o[obase + (long long)t * p.o_st + (long long)m * p.o_sk] = out_s[colm * L.Mp + m];
+                    if (t >= p.T) break;
+                    float* orow = o + (long long)t * p.o_st;
+                    const float* srow = out_s + colm * L.Mp;
+                    for (int m = lane; m < M; m += 32) {
+                        float v = srow[m];
+                        if (dbmode) {
+                            v = fmaxf(v, p.amin);
+                            R.runmax = fmaxf(R.runmax, v);
+                            v = p.db_mul * kb_log2(v) - p.db_sub;
+                        }
+                        if (sk == 1) orow[m] = v; else orow[(long long)m * sk] = v;
+                    }
                 }
             KB_PHASE_END
         }
@@ -330,6 +575,6 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
             if ((threadIdx.x & 31) == 0 && wm != 0u) kb_atomic_max_u32(p.item_max + b, wm);
 #endif
         }
-        KB_SYNC_CTA;  // sample / mag buffers are reused by the next tile
+        if (!fbmode) { KB_SYNC_WARP; }
     }
 }

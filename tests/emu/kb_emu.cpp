@@ -9,13 +9,25 @@
 #include "../../kapre_b200/csrc/stft_core.cuh"
 #include "../../kapre_b200/csrc/istft_core.cuh"
 
+template <int Q, int MODE>
+static void run_stft_qm(const KbStftParams& p, int n_cta) {
+    const KbStftSmem L = kb_stft_smem_layout(Q, p.n_fft, p.hop, p.TF, p.n_warps, p.mode, p.n_bands, p.n_chunks);
+    std::vector<char> raw(L.total + 64 + 16);
+    char* smem = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(raw.begin(), raw.end(), (char)0x7f);  // poison: catches reads of unwritten smem
+        kb_stft_cta<Q, MODE>(p, smem, cta, n_cta);
+    }
+}
+
 template <int Q>
 static void run_stft(const KbStftParams& p, int n_cta) {
-    const KbStftSmem L = kb_stft_smem_layout(Q, p.n_fft, p.hop, p.TF, p.n_warps, p.mode, p.n_bands);
-    std::vector<char> smem(L.total + 64);
-    for (int cta = 0; cta < n_cta; ++cta) {
-        std::fill(smem.begin(), smem.end(), (char)0x7f);  // poison: catches reads of unwritten smem
-        kb_stft_cta<Q>(p, smem.data(), cta, n_cta);
+    switch (p.mode) {
+        case KB_OUT_COMPLEX: run_stft_qm<Q, KB_OUT_COMPLEX>(p, n_cta); break;
+        case KB_OUT_MAG: run_stft_qm<Q, KB_OUT_MAG>(p, n_cta); break;
+        case KB_OUT_MAG_DB: run_stft_qm<Q, KB_OUT_MAG_DB>(p, n_cta); break;
+        case KB_OUT_FB: run_stft_qm<Q, KB_OUT_FB>(p, n_cta); break;
+        case KB_OUT_FB_DB: run_stft_qm<Q, KB_OUT_FB_DB>(p, n_cta); break;
     }
 }
 
@@ -35,23 +47,29 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
                 int n_fft, int win_length, int hop, int pad_left, int T, const float* window,
                 int mode, void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk,
                 const float* fb, int n_freq, int n_bands, float amin, float db_mul, float db_sub,
-                unsigned int* item_max, int TF, int n_warps, int n_cta) {
+                unsigned int* item_max, int TF, int n_warps, int n_cta, int dbuf, int bulk, long long x_numel) {
     const int Q = kb_q_for_nfft(n_fft);
     if (!Q) return -1;
+    if ((mode == KB_OUT_FB || mode == KB_OUT_FB_DB) && TF != n_warps * (32 / Q)) return -2;  // kernel contract
+    if (TF % (32 / Q)) return -2;
     std::vector<float> wh;
     std::vector<float2> twp, twn;
     std::vector<KbBand> bands;
     std::vector<float> fbw;
+    std::vector<kb_f4> cw; std::vector<kb_i2> cm; std::vector<int> cg;
     kb_make_wh(window, win_length, n_fft, wh);
     kb_make_twp(Q, twp);
     kb_make_twn(n_fft, twn);
-    if (fb) kb_make_bands(fb, n_freq, n_bands, bands, fbw);
+    if (fb) { kb_make_bands(fb, n_freq, n_bands, bands, fbw); kb_make_fb_chunks(fb, n_freq, n_bands, Q, cw, cm, cg); }
     KbStftParams p{};
     p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
     p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left;
     p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data();
     p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
     p.bands = fb ? bands.data() : nullptr; p.fbw = fb ? fbw.data() : nullptr; p.n_bands = fb ? n_bands : 0;
+    p.n_fbw = fb ? (int)fbw.size() : 0;
+    if (fb) { p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
+    p.x_lo = x; p.x_hi = x + x_numel; p.bulk_ok = (bulk && x_sl == 1) ? 1 : 0; p.dbuf = dbuf;
     p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max;
     p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
     switch (Q) {

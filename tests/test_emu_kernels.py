@@ -1,0 +1,101 @@
+"""CPU tier: the CUDA kernel bodies (the exact source nvcc compiles, run through the phase
+emulation of tests/emu) against the float64 oracle.  No GPU needed."""
+import numpy as np
+import pytest
+
+import emu_harness as E
+import oracle as O
+
+
+def nerr(a, b):
+    return float(np.abs(a - b).max() / max(float(np.abs(b).max()), 1e-30))
+
+
+def wave(rng, B, C, L, fmt):
+    return rng.uniform(-1, 1, size=(B, C, L) if fmt == 'channels_first' else (B, L, C)).astype(np.float32)
+
+
+@pytest.mark.parametrize('n_fft,hop,win', [(1024, 256, 1024), (512, 256, 512), (2048, 1024, 2018), (256, 64, 200),
+                                           (1024, 250, 1024), (512, 125, 400)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('pads', [(False, False), (True, True)])
+def test_emu_stft_complex_and_mag(n_fft, hop, win, fmt, pads):
+    rng = np.random.default_rng(n_fft + hop)
+    x = wave(rng, 2, 3, 5003, fmt)  # odd length: item bases hit every 4 B alignment class
+    w = O.get_window(None, win).astype(np.float32)
+    ref = O.stft_layer(x, n_fft, win, hop, None, pads[0], pads[1], fmt, fmt)
+    out, _ = E.emu_stft(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_COMPLEX, fmt, fmt, TF=16, n_warps=4)
+    assert out.shape == ref.shape
+    assert nerr(out, ref) < 1e-6
+    mag, _ = E.emu_stft(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_MAG, fmt, fmt, TF=8, n_warps=2, dbuf=0)
+    assert nerr(mag, np.abs(ref)) < 1e-6
+
+
+@pytest.mark.parametrize('dbuf,bulk', [(0, 1), (0, 0)])
+@pytest.mark.parametrize('L', [4000, 4001, 4002, 4003])
+def test_emu_staging_paths(dbuf, bulk, L):
+    """TMA-style 16 B-rounded staging (emulated as memcpy) for every alignment of the item base,
+    against the cooperative loader; pad regions next to the valid range must stay zero."""
+    rng = np.random.default_rng(L)
+    x = wave(rng, 3, 2, L, 'channels_first')
+    w = O.get_window('hamming_window', 512).astype(np.float32)
+    ref = O.stft_layer(x, 512, 512, 128, 'hamming_window', True, True, 'channels_first', 'channels_first')
+    out, _ = E.emu_stft(x, 512, 512, 128, w, True, True, E.MODE_COMPLEX, 'channels_first', 'channels_first',
+                        TF=8, n_warps=2, n_cta=2, dbuf=dbuf, bulk=bulk)
+    assert nerr(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize('n_fft,hop,n_mels,sr,TF,nw', [(1024, 256, 128, 22050, 16, 8), (1024, 256, 128, 22050, 8, 4),
+                                                        (512, 256, 40, 22050, 16, 4), (2048, 512, 64, 44100, 8, 8),
+                                                        (2048, 512, 128, 44100, 4, 4), (256, 64, 20, 16000, 32, 4),
+                                                        (512, 128, 64, 16000, 8, 2), (1024, 256, 80, 16000, 4, 2)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_emu_mel_and_db(n_fft, hop, n_mels, sr, TF, nw, fmt):
+    rng = np.random.default_rng(n_mels)
+    B = 2
+    x = wave(rng, B, 2, 6001, fmt)
+    x[1] *= 1e-3
+    w = O.get_window(None, n_fft).astype(np.float32)
+    fb = O.filterbank_mel(sr, n_fft // 2 + 1, n_mels, 0.0, None, False, 'slaney')
+    kw = dict(n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels, input_data_format=fmt, output_data_format=fmt)
+    ref = O.melspectrogram_layer(x, **kw)
+    out, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw)
+    assert nerr(out, ref) < 1e-6
+    refdb = O.melspectrogram_layer(x, return_decibel=True, db_dynamic_range=1e9, **kw)
+    outdb, imax = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB_DB, fmt, fmt, fb=fb, TF=TF, n_warps=nw)
+    assert np.abs(outdb - refdb).max() < 5e-5
+    np.testing.assert_allclose(imax, np.maximum(ref.reshape(B, -1).max(1), 1e-5), rtol=1e-6)
+    sm = O.stft_magnitude_layer(x, n_fft, None, hop, return_decibel=True, db_dynamic_range=1e9,
+                                input_data_format=fmt, output_data_format=fmt)
+    smo, imax2 = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_MAG_DB, fmt, fmt, TF=2 * TF, n_warps=nw)
+    lin = O.stft_magnitude_layer(x, n_fft, None, hop, input_data_format=fmt, output_data_format=fmt)
+    sig = lin > 1e-4 * lin.reshape(B, -1).max(1).reshape(B, 1, 1, 1)
+    assert np.abs(smo - sm)[sig].max() < 1e-3
+    np.testing.assert_allclose(imax2, lin.reshape(B, -1).max(1), rtol=1e-6)
+
+
+def test_emu_log_filterbank_dense_bands():
+    rng = np.random.default_rng(9)
+    x = wave(rng, 1, 1, 4000, 'channels_first')
+    fb = O.filterbank_log(22050, 513, 84, 12)
+    ref = O.apply_filterbank(np.abs(O.stft_layer(x, 1024, None, 256, input_data_format='channels_first',
+                                                 output_data_format='channels_first')), fb.astype(np.float64), 'channels_first')
+    out, _ = E.emu_stft(x, 1024, 1024, 256, O.get_window(None, 1024), False, False, E.MODE_FB, 'channels_first',
+                        'channels_first', fb=fb, TF=8, n_warps=4)
+    assert nerr(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize('n_fft,hop,win,TFc,nw', [(1024, 256, 1024, 16, 4), (2048, 1024, 2048, 8, 4), (2048, 256, 2048, 24, 4),
+                                                   (512, 128, 400, 12, 2), (256, 100, 256, 9, 2)])
+@pytest.mark.parametrize('ifmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('ofmt', ['channels_first', 'channels_last'])
+def test_emu_istft(n_fft, hop, win, TFc, nw, ifmt, ofmt):
+    rng = np.random.default_rng(n_fft + hop)
+    B, C, T, F = 2, 2, 37, n_fft // 2 + 1
+    shp = (B, C, T, F) if ifmt == 'channels_first' else (B, T, F, C)
+    X = (rng.normal(size=shp) + 1j * rng.normal(size=shp)).astype(np.complex64)
+    dual = O.inverse_stft_window(win, hop, O.get_window(None, win))
+    ref = O.istft_layer(X, n_fft, win, hop, None, ifmt, ofmt)
+    y = E.emu_istft(X, n_fft, win, hop, dual, ifmt, ofmt, TFc=TFc, n_warps=nw, n_cta=2)
+    assert y.shape == ref.shape
+    assert nerr(y, ref) < 1e-6

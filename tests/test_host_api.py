@@ -1,0 +1,156 @@
+"""CPU tier: host-side logic of the kapre-compatible API (no GPU compute) and the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def K():
+    import kapre_b200
+    return kapre_b200
+
+
+def test_import_surface(K):
+    # hot-path subset of kapre/__init__.py:8-36
+    for name in ('STFT', 'InverseSTFT', 'Magnitude', 'MagnitudeToDecibel', 'ApplyFilterbank', 'Phase',
+                 'get_melspectrogram_layer', 'get_stft_magnitude_layer', 'get_perfectly_reconstructing_stft_istft',
+                 'get_log_frequency_spectrogram_layer', 'backend', 'composed'):
+        assert hasattr(K, name)
+    import kapre
+    assert kapre.STFT is K.STFT and kapre.composed.get_melspectrogram_layer is K.get_melspectrogram_layer
+
+
+def test_stft_defaults_and_config(K):
+    l = K.STFT()
+    assert (l.n_fft, l.win_length, l.hop_length) == (2048, 2048, 512)  # hop = win // 4, time_frequency.py:128-129
+    assert l.input_data_format == 'channels_last' and l.output_data_format == 'channels_last'
+    l = K.STFT(n_fft=1000, win_length=400, name='foo', input_data_format='channels_first')
+    assert l.hop_length == 100
+    cfg = l.get_config()
+    for key in ('n_fft', 'win_length', 'hop_length', 'window_name', 'pad_begin', 'pad_end', 'input_data_format',
+                'output_data_format', 'name', 'trainable', 'dtype'):
+        assert key in cfg
+    assert cfg['output_data_format'] == 'default' and cfg['input_data_format'] == 'channels_first'
+    l2 = K.STFT.from_config(cfg)
+    assert l2.get_config() == cfg
+    i = K.InverseSTFT(n_fft=512, hop_length=128, forward_window_name='hamming_window')
+    assert set(i.get_config()) >= {'n_fft', 'win_length', 'hop_length', 'forward_window_name', 'input_data_format',
+                                   'output_data_format'}
+    d = K.MagnitudeToDecibel(ref_value=2.0, amin=1e-3, dynamic_range=50.0).get_config()
+    assert (d['ref_value'], d['amin'], d['dynamic_range']) == (2.0, 1e-3, 50.0)
+
+
+def test_validation_errors(K):
+    for cls in (K.STFT, K.InverseSTFT):
+        with pytest.raises(ValueError):
+            cls(input_data_format='weird_string')        # tests/test_time_frequency.py:645-654
+        with pytest.raises(ValueError):
+            cls(output_data_format='weird_string')
+        with pytest.raises(TypeError):
+            cls(input_data_format={'config': 'channels_last'})  # validated before the dict unwrap
+    with pytest.raises(ValueError):
+        K.ApplyFilterbank(type='mel', filterbank_kwargs={'sample_rate': 22050, 'n_freq': 257}, data_format='weird')
+    with pytest.raises(NotImplementedError):
+        K.backend.get_window_fn('wrong_window_name')     # tests/test_backend.py:127-129
+    with pytest.raises(ValueError):
+        K.backend.validate_data_format_str('weird_string')
+    with pytest.raises(RuntimeError):
+        K.backend.filterbank_log(sample_rate=22050, n_freq=513, n_bins=300, bins_per_octave=12)
+    with pytest.raises(ValueError):
+        K.get_melspectrogram_layer(input_data_format='nope')
+    # parameters of MagnitudeToDecibel are only checked when it is called (backend.py:168-173)
+    K.MagnitudeToDecibel(amin=-1.0)
+    with pytest.raises(ValueError):
+        K.backend.magnitude_to_decibel(np.ones(4, np.float32), amin=-1.0)
+
+
+@pytest.mark.parametrize('sample_rate', [44100, 22050])
+@pytest.mark.parametrize('n_freq', [1025, 257])
+@pytest.mark.parametrize('n_mels', [32, 128])
+@pytest.mark.parametrize('f_min', [0.0, 200])
+@pytest.mark.parametrize('f_max_ratio', [1.0, 0.5])
+@pytest.mark.parametrize('htk', [True, False])
+@pytest.mark.parametrize('norm', [None, 'slaney', 1.0])
+def test_mel(K, sample_rate, n_freq, n_mels, f_min, f_max_ratio, htk, norm):
+    """Mirror of tests/test_backend.py:43-75 with the oracle's librosa restatement as reference."""
+    f_max = int(f_max_ratio * (sample_rate // 2))
+    fb = K.backend.filterbank_mel(sample_rate=sample_rate, n_freq=n_freq, n_mels=n_mels, f_min=f_min, f_max=f_max,
+                                  htk=htk, norm=norm)
+    ref = O.filterbank_mel(sample_rate, n_freq, n_mels, f_min, f_max, htk, norm)
+    assert fb.dtype == np.float32 and fb.shape == (n_freq, n_mels)
+    np.testing.assert_allclose(ref, fb, rtol=1e-6, atol=1e-10)
+
+
+def test_log_filterbank_and_windows(K):
+    fb = K.backend.filterbank_log(22050, 513, 84, 12)
+    assert fb.shape == (513, 84) and fb.dtype == np.float32   # tests/test_backend.py:78-96
+    np.testing.assert_allclose(fb, O.filterbank_log(22050, 513, 84, 12), rtol=1e-6, atol=1e-12)
+    for name in (None, 'hann_window', 'hamming_window'):
+        for W in (1, 7, 512, 1000):
+            np.testing.assert_allclose(K.backend.get_window_fn(name)(W), O.get_window(name, W), atol=1e-7)
+    for name in ('kaiser_window', 'kaiser_bessel_derived_window', 'vorbis_window'):
+        w = K.backend.get_window_fn(name)(512)
+        assert w.shape == (512,) and np.isfinite(w).all() and w.max() <= 1.0 + 1e-6
+    dual = K.backend.inverse_stft_window_fn(256, K.backend.get_window_fn(None))(1024)
+    np.testing.assert_allclose(dual, O.inverse_stft_window(1024, 256, O.get_window(None, 1024)), atol=1e-6)
+
+
+def test_composed_structure_and_fusion_plan(K):
+    m = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, return_decibel=True, name='mel')
+    assert [type(l).__name__ for l in m.layers] == ['STFT', 'Magnitude', 'ApplyFilterbank', 'MagnitudeToDecibel']
+    assert m.name == 'mel' and m.layers[2].filterbank.shape == (513, 128)
+    m2 = K.Sequential.from_config(m.get_config())
+    assert m2.get_config() == m.get_config()
+    s = K.get_stft_magnitude_layer(n_fft=512)
+    assert [type(l).__name__ for l in s.layers] == ['STFT', 'Magnitude']
+    stft, istft = K.get_perfectly_reconstructing_stft_istft(1024, 256, 'channels_last', 'channels_first')
+    assert stft.pad_begin and stft.pad_end and stft.window_name == 'hann_window'
+    assert istft.input_data_format == 'channels_first' and istft.output_data_format == 'channels_last'
+
+
+def test_no_cpu_fallback(K):
+    """The product path must fail loudly without a GPU instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from kapre_b200 import _native
+    with pytest.raises(_native.KapreNativeError):
+        K.get_melspectrogram_layer(n_fft=512)(np.zeros((1, 4000, 1), np.float32))
+    with pytest.raises(_native.KapreNativeError):
+        K.backend.magnitude_to_decibel(np.ones((2, 3), np.float32))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'kapre_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(import|from)\s+oracle', text, re.M), f
+
+
+def test_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports everything include/kapre_b200.h declares."""
+    from kapre_b200 import _native
+    lib = _native.lib()
+    header = open(os.path.join(ROOT, 'include', 'kapre_b200.h')).read()
+    declared = set(re.findall(r'\b(kapre_[a-z_0-9]+)\s*\(', header))
+    declared -= {'kapre_wave_desc', 'kapre_spec_desc', 'kapre_db_cfg'}
+    bound = {name for name, _, _ in _native.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.kapre_version() == 100
+    assert lib.kapre_launch_count() == 0 or lib.kapre_launch_count() > 0
+    # argument validation happens before any CUDA call
+    out = ctypes.c_void_p()
+    w = np.ones(8, np.float32)
+    rc = lib.kapre_stft_plan_create(0, 8, 2, w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(out))
+    assert rc == -1 and b'out of range' in lib.kapre_last_error()

@@ -1,0 +1,29 @@
+"""Runs a few launches of one cfg2 configuration (for ncu).  MODE env: meldb | mel | mag | stft | istft."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kapre_b200 as K
+
+mode = os.environ.get('MODE', 'meldb')
+n = int(os.environ.get('N', '3'))
+torch.cuda.set_device(0)
+B, L = 256, 110250
+x = torch.rand((B, L, 1), device='cuda') * 2 - 1
+if mode == 'meldb':
+    layer = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128, return_decibel=True)
+elif mode == 'mel':
+    layer = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128)
+elif mode == 'mag':
+    layer = K.get_stft_magnitude_layer(n_fft=1024, hop_length=256)
+elif mode == 'stft':
+    layer = K.STFT(n_fft=1024, hop_length=256)
+elif mode == 'istft':
+    stft, layer = K.get_perfectly_reconstructing_stft_istft(1024, 256, 'channels_last', 'channels_last')
+    x = stft(x[:128, :16000])
+for _ in range(n):
+    y = layer(x)
+torch.cuda.synchronize()
+print(mode, tuple(y.shape), K._native.last_launch_info())

@@ -9,6 +9,18 @@ import kapre_b200 as K
 from kapre_b200 import _native
 
 
+try:
+    import pynvml
+    pynvml.nvmlInit()
+    _h = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+    def sm_clock():
+        return pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM)
+except Exception:  # pragma: no cover
+    def sm_clock():
+        return -1
+
+
 def time_it(fn, iters=20, warm=3):
     for _ in range(warm):
         fn()
@@ -18,7 +30,9 @@ def time_it(fn, iters=20, warm=3):
     for _ in range(iters):
         fn()
     e1.record()
+    clk = sm_clock()
     torch.cuda.synchronize()
+    time_it.clk = clk
     return e0.elapsed_time(e1) / iters
 
 
@@ -34,20 +48,20 @@ def main():
             ('mel', K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128)),
             ('mag', K.get_stft_magnitude_layer(n_fft=1024, hop_length=256)),
             ('stft', K.STFT(n_fft=1024, hop_length=256))):
-        for nw in (4, 8):
-            for tf in (8, 16, 32):
-                os.environ['KAPRE_B200_TF'] = str(tf)
-                os.environ['KAPRE_B200_NW'] = str(nw)
+        fb = name.startswith('mel')
+        for nw, tf in [(nw, tf) for nw in (2, 4, 8) for tf in ((0,) if fb else (8, 16, 32))]:
+            os.environ['KAPRE_B200_TF'] = str(tf)
+            os.environ['KAPRE_B200_NW'] = str(nw)
 
-                def fn():
-                    cnt[0] += 1
-                    return layer(xs[cnt[0] % 3])
-                try:
-                    ms = time_it(fn)
-                    print('%-6s TF=%2d NW=%d  %.3f ms  %.3e frames/s  [%s]' % (name, tf, nw, ms, frames / ms * 1e3,
-                                                                              _native.last_launch_info()), flush=True)
-                except Exception as e:  # config does not fit
-                    print('%-6s TF=%2d NW=%d  n/a (%s)' % (name, tf, nw, str(e)[:60]), flush=True)
+            def fn():
+                cnt[0] += 1
+                return layer(xs[cnt[0] % 3])
+            try:
+                ms = time_it(fn)
+                print('%-6s TF=%2d NW=%d  %.3f ms  %.3e frames/s  clk=%d [%s]' % (name, tf, nw, ms, frames / ms * 1e3, time_it.clk,
+                                                                          _native.last_launch_info()), flush=True)
+            except Exception as e:  # config does not fit
+                print('%-6s TF=%2d NW=%d n/a (%s)' % (name, tf, nw, str(e)[:60]), flush=True)
     os.environ.pop('KAPRE_B200_TF'); os.environ.pop('KAPRE_B200_NW')
     # inverse
     stft, istft = K.get_perfectly_reconstructing_stft_istft(1024, 256, 'channels_last', 'channels_last')
