@@ -495,7 +495,8 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     KbStftParams p{};
     p.x = x_dev; p.x_sb = xd->stride_b; p.x_sc = xd->stride_c; p.x_sl = xd->stride_l;
     p.B = B; p.C = C; p.L = Ln; p.n_fft = plan->n_fft; p.hop = plan->hop; p.T = T; p.pad_left = pad_left;
-    p.x_lo = x_dev; p.x_hi = x_dev + max_off + 1; p.bulk_ok = bulk ? 1 : 0; p.dbuf = 0;
+    p.x_lo = x_dev; p.x_hi = x_dev + max_off + 1; p.x_numel = max_off + 1;
+    p.x_align = (unsigned)(((uintptr_t)x_dev >> 2) & 3); p.bulk_ok = bulk ? 1 : 0; p.dbuf = 0;
     p.wh = plan->wh; p.twp = plan->twp; p.twn = plan->twn;
     p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
     p.mode = mode;
@@ -661,7 +662,7 @@ int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre
     f->Q = kb_q_for_nfft((n_freq - 1) * 2);
     if (f->Q) {
         std::vector<kb_f4> cw; std::vector<kb_i2> cm; std::vector<int> cg;
-        kb_make_fb_chunks(fb_host, n_freq, n_bands, f->Q, cw, cm, cg);
+        kb_make_fb_chunks(fb_host, n_freq, n_bands, 32, cw, cm, cg);
         f->n_chunks = (int)cw.size();
         if ((rc = kb_upload(cw, &f->cw)) || (rc = kb_upload(cm, &f->cm)) || (rc = kb_upload(cg, &f->cg))) {
             kapre_filterbank_destroy(f); return rc;

@@ -47,6 +47,8 @@ struct KbStftParams {
     // stay inside it.  bulk_ok: x_sl == 1 and x is 4 B-aligned (else the fallback loader runs).
     const void* x_lo;
     const void* x_hi;
+    long long x_numel;   // elements addressable from x (max element offset + 1)
+    unsigned x_align;    // ((uintptr_t)x >> 2) & 3: position of x inside its 16 B line, in floats
     int bulk_ok;
     int dbuf;            // 1: two sample buffers (next tile prefetched during the current one)
     // transform
@@ -66,7 +68,7 @@ struct KbStftParams {
     const float* fbw;
     int n_bands;
     int n_fbw;           // floats in fbw (bands are padded to multiples of 4 weights)
-    // the same filterbank as flat lists of 4-weight chunks, one list per lane group (Q groups):
+    // the same filterbank as flat lists of 4-weight chunks, one list per lane group (32 groups):
     // chunk i multiplies bins [cm[i].x, cm[i].x + 4); cm[i].y is the band to store after this
     // chunk (its last one) or -1.  Group g owns chunks [cg[g], cg[g+1]).
     const kb_f4* cw;

@@ -54,7 +54,7 @@ KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_wa
     s.twn = off; off += kb_align16((P / 2) * 8);
     s.cw = off; if (fb) off += n_chunks * 16;
     s.cm = off; if (fb) off += kb_align16(n_chunks * 8);
-    s.cg = off; if (fb) off += kb_align16((Q + 1) * 4);
+    s.cg = off; if (fb) off += kb_align16(33 * 4);
     s.bar = off; off += 16;
     s.span = (TF - 1) * hop + n_fft;
     s.Mp = n_bands | 1;
@@ -128,7 +128,7 @@ KB_D void kb_bar_wait(KbBar* bar, unsigned parity) {
 // so every thread computes the same plan (no broadcast needed).
 struct KbTilePlan {
     int b, c, t0;
-    long long s_first;   // first padded-signal sample of the tile (may be negative: pad_begin)
+    int s_first;         // first padded-signal sample of the tile (may be negative: pad_begin)
     int v0, v1;          // valid (non-pad) range in tile coordinates [v0, v1), v0 == v1: all pad
     int shift;           // smem index of tile sample i is i + shift
     int bulk;            // 1: one TMA bulk copy, 0: cooperative loads
@@ -138,33 +138,34 @@ struct KbTilePlan {
 };
 
 KB_HD KbTilePlan kb_plan_tile(const KbStftParams& p, int span, int tile) {
+    // Executed by every thread once or twice per tile, so it is kept to 32-bit arithmetic
+    // except for the final pointer.
     KbTilePlan t;
-    const int sig = tile / p.n_tiles_t;
-    const int tt = tile - sig * p.n_tiles_t;
-    t.b = sig / p.C;
-    t.c = sig - t.b * p.C;
+    const unsigned sig = (unsigned)tile / (unsigned)p.n_tiles_t;
+    const int tt = tile - (int)sig * p.n_tiles_t;
+    if (p.C == 1) { t.b = (int)sig; t.c = 0; }
+    else { t.b = (int)(sig / (unsigned)p.C); t.c = (int)sig - t.b * p.C; }
     t.t0 = tt * p.TF;
-    t.s_first = (long long)t.t0 * p.hop - p.pad_left;
-    long long a = -t.s_first, e = (long long)p.L - t.s_first;
+    const int s_first = t.t0 * p.hop - p.pad_left;      // host guarantees T*hop + n_fft < 2^31
+    t.s_first = s_first;
+    int a = -s_first, e = p.L - s_first;
     if (a < 0) a = 0;
     if (e > span) e = span;
     if (e < a) e = a;
-    t.v0 = (int)a; t.v1 = (int)e;
+    t.v0 = a; t.v1 = e;
     t.shift = 0; t.bulk = 0; t.src = nullptr; t.dst = 0; t.bytes = 0;
-    if (p.x_sl == 1 && p.bulk_ok && t.v1 > t.v0) {
-        const float* xsig = p.x + (long long)t.b * p.x_sb + (long long)t.c * p.x_sc;
-        const float* g0 = xsig + (t.s_first + t.v0);            // first valid sample
-        const float* g1 = xsig + (t.s_first + t.v1);            // one past the last valid sample
-        const uintptr_t a0 = (uintptr_t)g0 & ~(uintptr_t)15;
-        const uintptr_t a1 = ((uintptr_t)g1 + 15) & ~(uintptr_t)15;
-        if (a0 >= (uintptr_t)p.x_lo && a1 <= (uintptr_t)p.x_hi) {
-            const int head = (int)(((uintptr_t)g0 - a0) >> 2);  // 0..3 floats fetched before v0
-            t.shift = (head - t.v0) & 3;                        // makes (v0 + shift - head) % 4 == 0
+    if (p.bulk_ok && e > a) {
+        // element offsets of the first / one-past-last valid sample inside the waveform tensor
+        const long long off0 = (long long)t.b * p.x_sb + (long long)t.c * p.x_sc + (s_first + a);
+        const int head = (int)((p.x_align + (unsigned)off0) & 3u);           // floats before v0 in its 16 B line
+        const int tail = (int)((0u - (p.x_align + (unsigned)off0 + (unsigned)(e - a))) & 3u);
+        const long long lo = off0 - head, hi = off0 + (e - a) + tail;        // rounded range, in elements
+        if (lo >= 0 && hi <= p.x_numel) {
+            t.shift = (head - a) & 3;                                       // (v0 + shift - head) % 4 == 0
             t.bulk = 1;
-            t.src = reinterpret_cast<const float*>(a0);
-            t.dst = t.v0 + t.shift - head;
-            t.bytes = (int)(a1 - a0);
-            if (t.dst < 0) { t.shift += 4; t.dst += 4; }
+            t.src = p.x + lo;
+            t.dst = a + t.shift - head;
+            t.bytes = (int)(hi - lo) * 4;
         }
     }
     return t;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void kb_issue_tile_loads(const KbStftParams& p, const
         for (int i = tid; i < t.v0 - 4; i += nt) s[i] = 0.0f;
         for (int i = t.v1 + 4 + tid; i < span; i += nt) s[i] = 0.0f;
     } else {
-        const float* xsig = p.x + (long long)t.b * p.x_sb + (long long)t.c * p.x_sc + t.s_first * p.x_sl;
+        const float* xsig = p.x + (long long)t.b * p.x_sb + (long long)t.c * p.x_sc + (long long)t.s_first * p.x_sl;
         int i = tid;
         for (; i + 3 * nt < span; i += 4 * nt) {   // 4 independent loads in flight per thread
             float v[4];
@@ -236,6 +237,23 @@ KB_HD float kb_band_dot(const float* __restrict__ w, const float* __restrict__ m
         mc += 4 * FPW;
     }
     return (a0 + a1) + (a2 + a3);
+}
+
+// FPW consecutive floats (FPW in {1,2,4,8}) from a FPW*4-byte aligned shared address.
+template <int FPW>
+KB_HD void kb_load_vec(float* dst, const float* src) {
+    if constexpr (FPW == 1) {
+        dst[0] = src[0];
+    } else if constexpr (FPW == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(src);
+        dst[0] = v.x; dst[1] = v.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < FPW / 4; ++j) {
+            const kb_f4 v = reinterpret_cast<const kb_f4*>(src)[j];
+            dst[4 * j] = v.x; dst[4 * j + 1] = v.y; dst[4 * j + 2] = v.z; dst[4 * j + 3] = v.w;
+        }
+    }
 }
 
 // One CTA's share of the work: tiles cta, cta + n_cta, ...
@@ -288,7 +306,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
         if (fbmode) {
             for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
-            for (int i = tid; i <= Q; i += kb_nt) cg_s[i] = p.cg[i];
+            for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.cg[i];
         }
     KB_PHASE_END
     KB_SYNC_CTA;
@@ -511,31 +529,42 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                     kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
                 KB_PHASE_END
             }
-            // ---- phase 5: filterbank, one lane per frame column (uniform weights) ----------
+            // ---- phase 5: filterbank ------------------------------------------------------------
+            // 32 lane groups of NW lanes; lane w of a group owns the FPW frame columns held in warp
+            // w's exchange region (one vector load per bin), the group walks its list of 4-bin chunks.
             KB_PHASE_BEGIN
                 (void)R;
                 const int warp = tid >> 5, lane = tid & 31;
-                const int cpw = TF < 32 ? TF : 32;     // columns per warp
-                const int subs = 32 / cpw;             // band sub-groups per warp
-                const int colm = lane % cpw, sub = lane / cpw;
-                const float* __restrict__ mcol = reinterpret_cast<const float*>(ex_s + (colm / FPW) * EXS) + (colm % FPW);
-                float* __restrict__ orow_s = out_s + colm * L.Mp;
-                const int grp = warp * subs + sub;          // lane group: Q of them per CTA
-                if (grp < Q) {
-                    const int ce = cg_s[grp + 1];
-                    float a0 = 0.0f, a1 = 0.0f;
-                    for (int i = cg_s[grp]; i < ce; ++i) {
-                        const kb_f4 w = cw_s[i];            // 16 B, uniform within the lane group
-                        const kb_i2 mt = cm_s[i];
-                        const float* mc = mcol + mt.x * FPW;
-                        a0 += w.x * mc[0];
-                        a1 += w.y * mc[FPW];
-                        a0 += w.z * mc[2 * FPW];
-                        a1 += w.w * mc[3 * FPW];
-                        if (mt.y >= 0) {
-                            orow_s[mt.y] = a0 + a1;
-                            a0 = 0.0f;
-                            a1 = 0.0f;
+                const int w = lane % NW;
+                const int grp = warp * (32 / NW) + lane / NW;           // 0..31
+                const float* __restrict__ mw = reinterpret_cast<const float*>(ex_s + w * EXS);
+                float* __restrict__ ocol = out_s + (w * FPW) * L.Mp;
+                float a0[FPW], a1[FPW];
+#pragma unroll
+                for (int g = 0; g < FPW; ++g) { a0[g] = 0.0f; a1[g] = 0.0f; }
+                const int ce = cg_s[grp + 1];
+                for (int i = cg_s[grp]; i < ce; ++i) {
+                    const kb_f4 wv = cw_s[i];                             // 16 B, uniform within the group
+                    const kb_i2 mt = cm_s[i];
+                    const float* mp = mw + mt.x * FPW;
+                    float m0[FPW], m1[FPW], m2[FPW], m3[FPW];
+                    kb_load_vec<FPW>(m0, mp);
+                    kb_load_vec<FPW>(m1, mp + FPW);
+                    kb_load_vec<FPW>(m2, mp + 2 * FPW);
+                    kb_load_vec<FPW>(m3, mp + 3 * FPW);
+#pragma unroll
+                    for (int g = 0; g < FPW; ++g) {
+                        a0[g] += wv.x * m0[g];
+                        a1[g] += wv.y * m1[g];
+                        a0[g] += wv.z * m2[g];
+                        a1[g] += wv.w * m3[g];
+                    }
+                    if (mt.y >= 0) {
+#pragma unroll
+                        for (int g = 0; g < FPW; ++g) {
+                            ocol[g * L.Mp + mt.y] = a0[g] + a1[g];
+                            a0[g] = 0.0f;
+                            a1[g] = 0.0f;
                         }
                     }
                 }

@@ -60,7 +60,7 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     kb_make_wh(window, win_length, n_fft, wh);
     kb_make_twp(Q, twp);
     kb_make_twn(n_fft, twn);
-    if (fb) { kb_make_bands(fb, n_freq, n_bands, bands, fbw); kb_make_fb_chunks(fb, n_freq, n_bands, Q, cw, cm, cg); }
+    if (fb) { kb_make_bands(fb, n_freq, n_bands, bands, fbw); kb_make_fb_chunks(fb, n_freq, n_bands, 32, cw, cm, cg); }
     KbStftParams p{};
     p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
     p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left;
@@ -69,7 +69,8 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     p.bands = fb ? bands.data() : nullptr; p.fbw = fb ? fbw.data() : nullptr; p.n_bands = fb ? n_bands : 0;
     p.n_fbw = fb ? (int)fbw.size() : 0;
     if (fb) { p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
-    p.x_lo = x; p.x_hi = x + x_numel; p.bulk_ok = (bulk && x_sl == 1) ? 1 : 0; p.dbuf = dbuf;
+    p.x_lo = x; p.x_hi = x + x_numel; p.x_numel = x_numel; p.x_align = (unsigned)(((uintptr_t)x >> 2) & 3);
+    p.bulk_ok = (bulk && x_sl == 1) ? 1 : 0; p.dbuf = dbuf;
     p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max;
     p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
     switch (Q) {
