@@ -25,16 +25,15 @@ KB_HD constexpr float kb_sin32(int t) { return t <= 8 ? kb_cos32_q(8 - t) : kb_c
 KB_HD cpx kb_twmul32(cpx d, int t) {
     if (t == 0) return d;
     if (t == 8) return cmake(d.im, -d.re);
-    if (t == 4) {
+    if (t == 4) {   // (1 - i)/sqrt2 :  ((re + im), (im - re)) * s
         const float s = 0.70710678118654752440f;
-        return cmake((d.re + d.im) * s, (d.im - d.re) * s);
+        return cscale(cadd(d, cmake(d.im, -d.re)), s);
     }
-    if (t == 12) {
+    if (t == 12) {  // (-1 - i)/sqrt2 : ((im - re), -(re + im)) * s
         const float s = 0.70710678118654752440f;
-        return cmake((d.im - d.re) * s, -(d.re + d.im) * s);
+        return cscale(csub(cmake(d.im, -d.re), d), s);
     }
-    const float c = kb_cos32(t), sn = kb_sin32(t);
-    return cmake(d.re * c + d.im * sn, d.im * c - d.re * sn);
+    return cmul_tw(d, kb_cos32(t), kb_sin32(t));
 }
 
 template <int R>

@@ -102,11 +102,94 @@ struct KbIstftParams {
     int n_warps;
 };
 
-struct cpx { float re, im; };
+// Complex number = one aligned register pair.  On sm_100a the arithmetic below compiles to the
+// packed fp32x2 instructions (SASS FADD2 / FMUL2 / FFMA2): one instruction per complex add,
+// two per complex multiply; ptxas folds the lane swaps / sign patterns into operand modifiers.
+struct alignas(8) cpx { float re, im; };
 KB_HD cpx cmake(float a, float b) { cpx r; r.re = a; r.im = b; return r; }
-KB_HD cpx cadd(cpx a, cpx b) { return cmake(a.re + b.re, a.im + b.im); }
-KB_HD cpx csub(cpx a, cpx b) { return cmake(a.re - b.re, a.im - b.im); }
-KB_HD cpx cmul(cpx a, cpx b) { return cmake(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+
+#if defined(__CUDA_ARCH__)
+typedef unsigned long long kb_u64;
+KB_D kb_u64 kb_pk(float lo, float hi) { kb_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+KB_D cpx kb_up(kb_u64 v) { cpx r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.re), "=f"(r.im) : "l"(v)); return r; }
+KB_D kb_u64 kb_add2(kb_u64 a, kb_u64 b) { kb_u64 r; asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+KB_D kb_u64 kb_sub2(kb_u64 a, kb_u64 b) { kb_u64 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+KB_D kb_u64 kb_mul2(kb_u64 a, kb_u64 b) { kb_u64 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+KB_D kb_u64 kb_fma2(kb_u64 a, kb_u64 b, kb_u64 c) { kb_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#endif
+
+KB_HD cpx cadd(cpx a, cpx b) {
+#if defined(__CUDA_ARCH__)
+    return kb_up(kb_add2(kb_pk(a.re, a.im), kb_pk(b.re, b.im)));
+#else
+    return cmake(a.re + b.re, a.im + b.im);
+#endif
+}
+KB_HD cpx csub(cpx a, cpx b) {
+#if defined(__CUDA_ARCH__)
+    return kb_up(kb_sub2(kb_pk(a.re, a.im), kb_pk(b.re, b.im)));
+#else
+    return cmake(a.re - b.re, a.im - b.im);
+#endif
+}
+// a + conj(b) and a - conj(b)
+KB_HD cpx cadd_conj(cpx a, cpx b) {
+#if defined(__CUDA_ARCH__)
+    return kb_up(kb_add2(kb_pk(a.re, a.im), kb_pk(b.re, -b.im)));
+#else
+    return cmake(a.re + b.re, a.im - b.im);
+#endif
+}
+KB_HD cpx csub_conj(cpx a, cpx b) {
+#if defined(__CUDA_ARCH__)
+    return kb_up(kb_sub2(kb_pk(a.re, a.im), kb_pk(b.re, -b.im)));
+#else
+    return cmake(a.re - b.re, a.im + b.im);
+#endif
+}
+// complex product a * b = a (.) (b.re, b.re) + swap(a) (.) (-b.im, b.im)
+KB_HD cpx cmul(cpx a, cpx b) {
+#if defined(__CUDA_ARCH__)
+    const kb_u64 t = kb_mul2(kb_pk(a.re, a.im), kb_pk(b.re, b.re));
+    return kb_up(kb_fma2(kb_pk(a.im, a.re), kb_pk(-b.im, b.im), t));
+#else
+    return cmake(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+#endif
+}
+// element-wise product (a.re * b.re, a.im * b.im): window multiply of two packed samples
+KB_HD cpx cmul_elem(cpx a, cpx b) {
+#if defined(__CUDA_ARCH__)
+    return kb_up(kb_mul2(kb_pk(a.re, a.im), kb_pk(b.re, b.im)));
+#else
+    return cmake(a.re * b.re, a.im * b.im);
+#endif
+}
+// a * s for a real scalar s
+KB_HD cpx cscale(cpx a, float s) {
+#if defined(__CUDA_ARCH__)
+    return kb_up(kb_mul2(kb_pk(a.re, a.im), kb_pk(s, s)));
+#else
+    return cmake(a.re * s, a.im * s);
+#endif
+}
+// d * (c - i sn): twiddle with separately given cosine / sine (compile-time constants at the call sites)
+KB_HD cpx cmul_tw(cpx d, float c, float sn) {
+#if defined(__CUDA_ARCH__)
+    const kb_u64 t = kb_mul2(kb_pk(d.re, d.im), kb_pk(c, c));
+    return kb_up(kb_fma2(kb_pk(d.im, d.re), kb_pk(sn, -sn), t));
+#else
+    return cmake(d.re * c + d.im * sn, d.im * c - d.re * sn);
+#endif
+}
+// |a|^2
+KB_HD float cnorm(cpx a) {
+#if defined(__CUDA_ARCH__)
+    const cpx q = kb_up(kb_mul2(kb_pk(a.re, a.im), kb_pk(a.re, a.im)));
+    return q.re + q.im;
+#else
+    return a.re * a.re + a.im * a.im;
+#endif
+}
 
 // shared-memory footprint helpers (bytes), shared by host launch code and kernels
 KB_HD int kb_align16(int v) { return (v + 15) & ~15; }

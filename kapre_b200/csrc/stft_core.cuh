@@ -355,9 +355,9 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n2 = 2 * (q + Q * j);
-                            const float2 xv = *reinterpret_cast<const float2*>(fr + n2);
-                            const float2 wv = *reinterpret_cast<const float2*>(wh_s + n2);
-                            R.v[j] = cmake(xv.x * wv.x, xv.y * wv.y);
+                            const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
+                            const cpx wv = *reinterpret_cast<const cpx*>(wh_s + n2);
+                            R.v[j] = cmul_elem(xv, wv);
                         }
                     } else {
 #pragma unroll
@@ -447,12 +447,11 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                             const cpx A = zf[k];
                             const cpx Bv = zf[kk & (P - 1)];
                             const cpx W = twn_s[k];
-                            const float Er = A.re + Bv.re, Ei = A.im - Bv.im;
-                            const float Dr = A.re - Bv.re, Di = A.im + Bv.im;
-                            const float Tr = W.re * Di + W.im * Dr;
-                            const float Ti = W.im * Di - W.re * Dr;
-                            X1 = cmake(Er + Tr, Ei + Ti);
-                            X2 = cmake(Er - Tr, Ti - Ei);
+                            const cpx E = cadd_conj(A, Bv);            // A + conj(B)
+                            const cpx D = csub_conj(A, Bv);            // A - conj(B)
+                            const cpx T = cmul(cmake(D.im, -D.re), W); // W * (-i D)
+                            X1 = cadd(E, T);
+                            X2 = csub(E, T);                           // conj(X[P-k]); sign of Im fixed on store
                         } else {  // bin P/2 pairs with itself; only lane 0's value is used
                             k = P / 2;
                             kk = -1;
@@ -465,15 +464,15 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                             if (valid) {
                                 if (sk == 1) {
                                     oc[k] = make_float2(X1.re, X1.im);
-                                    if (kk >= 0) oc[kk] = make_float2(X2.re, X2.im);
+                                    if (kk >= 0) oc[kk] = make_float2(X2.re, -X2.im);
                                 } else {
                                     oc[k * sk] = make_float2(X1.re, X1.im);
-                                    if (kk >= 0) oc[kk * sk] = make_float2(X2.re, X2.im);
+                                    if (kk >= 0) oc[kk * sk] = make_float2(X2.re, -X2.im);
                                 }
                             }
                         } else {
-                            float m1 = kb_sqrt(X1.re * X1.re + X1.im * X1.im);
-                            float m2 = kb_sqrt(X2.re * X2.re + X2.im * X2.im);
+                            float m1 = kb_sqrt(cnorm(X1));
+                            float m2 = kb_sqrt(cnorm(X2));
                             if (fbmode) {
                                 magr[(gg * (Q / 2 + 1) + i) * 2 + 0] = m1;
                                 magr[(gg * (Q / 2 + 1) + i) * 2 + 1] = m2;
