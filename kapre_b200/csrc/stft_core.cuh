@@ -28,7 +28,7 @@
 #include "fft_regs.cuh"
 
 struct KbStftSmem {
-    int wh, twp, twn, cw, cm, cg, bar, samples, outs, ex, total;  // byte offsets
+    int wh, twp, twn, cw, cm, cg, bar, plan, samples, outs, ex, total;  // byte offsets
     int span;       // samples staged per tile
     int exw;        // complex elements per warp in the exchange buffer (incl. bank skew)
     int Mp;         // padded band stride of out_s
@@ -56,6 +56,7 @@ KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_wa
     s.cm = off; if (fb) off += kb_align16(n_chunks * 8);
     s.cg = off; if (fb) off += kb_align16(33 * 4);
     s.bar = off; off += 16;
+    s.plan = off; off += 64;
     s.span = (TF - 1) * hop + n_fft;
     s.Mp = n_bands | 1;
     s.samples = off; off += kb_align16((s.span + 8) * 4);  // +4 front (alignment shift) +4 back (rounded copy)
@@ -282,6 +283,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     kb_i2* __restrict__ cm_s = reinterpret_cast<kb_i2*>(smem + L.cm);
     int* __restrict__ cg_s = reinterpret_cast<int*>(smem + L.cg);
     KbBar* bar = reinterpret_cast<KbBar*>(smem + L.bar);
+    KbTilePlan* plan_s = reinterpret_cast<KbTilePlan*>(smem + L.plan);   // next tile's plan (filterbank modes)
     float* smp0 = reinterpret_cast<float*>(smem + L.samples);
     float* __restrict__ out_s = reinterpret_cast<float*>(smem + L.outs);
     cpx* ex_s = reinterpret_cast<cpx*>(smem + L.ex);
@@ -320,7 +322,10 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     }
 
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
-        const KbTilePlan tp = kb_plan_tile(p, span, tile);
+        // filterbank modes: the plan was computed once when the tile's loads were issued and parked
+        // in shared memory (a CTA barrier lies in between); otherwise recompute it (cheap per frame
+        // there, tiles are larger)
+        const KbTilePlan tp = (fbmode && tile != cta) ? *plan_s : kb_plan_tile(p, span, tile);
         const int b = tp.b, c = tp.c, t0 = tp.t0;
         const long long obase = (long long)b * p.o_sb + (long long)c * p.o_sc;
         const float* __restrict__ smp_s = smp0 + tp.shift;
@@ -525,6 +530,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
                 KB_PHASE_BEGIN
                     (void)R;
+                    if (tid == 0) *plan_s = tn;
                     kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
                 KB_PHASE_END
             }
@@ -575,21 +581,28 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 float* o = reinterpret_cast<float*>(p.out) + obase;
                 const int M = p.n_bands;
                 const int sk = (int)p.o_sk;
+                const float amin = p.amin, dmul = p.db_mul, dsub = p.db_sub;
+                float rmax = R.runmax;
                 for (int colm = warp; colm < TF; colm += NW) {
                     const int t = t0 + colm;
                     if (t >= p.T) break;
-                    float* orow = o + (long long)t * p.o_st;
-                    const float* srow = out_s + colm * L.Mp;
+                    float* __restrict__ orow = o + (long long)t * p.o_st + (sk == 1 ? lane : lane * sk);
+                    const float* __restrict__ srow = out_s + colm * L.Mp + lane;
+                    const int step = 32 * sk;
+#pragma unroll 4
                     for (int m = lane; m < M; m += 32) {
-                        float v = srow[m];
+                        float v = *srow;
                         if (dbmode) {
-                            v = fmaxf(v, p.amin);
-                            R.runmax = fmaxf(R.runmax, v);
-                            v = p.db_mul * kb_log2(v) - p.db_sub;
+                            v = fmaxf(v, amin);
+                            rmax = fmaxf(rmax, v);
+                            v = dmul * kb_log2(v) - dsub;
                         }
-                        if (sk == 1) orow[m] = v; else orow[(long long)m * sk] = v;
+                        *orow = v;
+                        srow += 32;
+                        orow += step;
                     }
                 }
+                R.runmax = rmax;
             KB_PHASE_END
         }
 

@@ -331,3 +331,76 @@ def test_abi_errors_and_config(K):
     n0 = _native.launch_count()
     m(x)
     assert _native.launch_count() - n0 == 2  # fused kernel + clamp kernel
+
+
+# ------------------------------------------------------------------------------- other BASELINE configs at full size
+def test_cfg1_reference_cpu_case(K):
+    """BASELINE cfg1: batch 4, mono 16 kHz x 1 s, n_fft 512 hop 256 64 mel -- whole tensor vs oracle."""
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, size=(4, 16000, 1)).astype(np.float32)
+    kw = dict(n_fft=512, hop_length=256, sample_rate=16000, n_mels=64, return_decibel=True)
+    got = K.get_melspectrogram_layer(**kw).predict(x)
+    ref = O.melspectrogram_layer(x, **kw)
+    assert got.shape == ref.shape == (4, 61, 64, 1)
+    assert np.abs(got - ref).max() < 2e-4
+
+
+def test_cfg3_full_size_properties(K):
+    """BASELINE cfg3: batch 1024, 6 channels, 44.1 kHz x 1 s, channels_last, n_fft 2048 hop 1024,
+    magnitude + decibel (get_stft_magnitude_layer).  Spot-check items against the oracle and check
+    size-independent properties on the whole 1 GB tensor."""
+    g = torch.Generator(device='cuda').manual_seed(4321)
+    x = torch.rand((1024, 44100, 6), generator=g, device='cuda') * 2 - 1
+    x[7] *= 1e-3
+    kw = dict(n_fft=2048, hop_length=1024, return_decibel=True, input_data_format='channels_last',
+              output_data_format='channels_last')
+    layer = K.get_stft_magnitude_layer(**kw)
+    y = layer(x)
+    assert y.shape == (1024, 42, 1025, 6)
+    assert bool(torch.isfinite(y).all())
+    lin = K.get_stft_magnitude_layer(**dict(kw, return_decibel=False))(x[:8])
+    for i in (0, 7):
+        ref = O.stft_magnitude_layer(x[i:i + 1].cpu().numpy(), **kw)
+        sig = lin[i:i + 1].cpu().numpy() > 1e-4 * float(lin[i].max())
+        assert np.abs(y[i:i + 1].cpu().numpy() - ref)[sig].max() < 2e-3
+    # sharding property: any split of the batch reproduces the items bit for bit
+    assert torch.equal(layer(x[512:640]), y[512:640])
+    # channels are independent up to the shared per-item clamp (inactive here): permuting channels permutes outputs
+    perm = [3, 0, 5, 1, 4, 2]
+    assert torch.equal(layer(x[:16][:, :, perm]), y[:16][:, :, :, perm])
+    # channels_first output of the same data is the transpose
+    yf = K.get_stft_magnitude_layer(**dict(kw, output_data_format='channels_first'))(x[:16])
+    assert torch.equal(yf.permute(0, 2, 3, 1), y[:16])
+
+
+def test_cfg5_shard_full_size_properties(K):
+    """BASELINE cfg5, one GPU's shard: batch 1024, mono 16 kHz x 10 s, log-mel (n_fft 1024, hop 256, 128 mel)."""
+    g = torch.Generator(device='cuda').manual_seed(99)
+    x = torch.rand((1024, 160000, 1), generator=g, device='cuda') * 2 - 1
+    kw = dict(n_fft=1024, hop_length=256, sample_rate=16000, n_mels=128, return_decibel=True)
+    layer = K.get_melspectrogram_layer(**kw)
+    y = layer(x)
+    assert y.shape == (1024, 622, 128, 1)
+    assert bool(torch.isfinite(y).all())
+    for i in (0, 1023):
+        ref = O.melspectrogram_layer(x[i:i + 1].cpu().numpy(), **kw)
+        assert np.abs(y[i:i + 1].cpu().numpy() - ref).max() < 2e-4
+    # 8-way shard boundaries (the 8-GPU job) are bit-identical to the unsharded run
+    for r in (0, 3, 7):
+        assert torch.equal(layer(x[r * 128:(r + 1) * 128]), y[r * 128:(r + 1) * 128])
+    # scaling the waveform by 2 adds 10*log10(2) dB everywhere above the amin floor
+    y2 = layer(2.0 * x[:32])
+    above = y[:32] > -49.0
+    assert float(((y2 - y[:32]) - 10.0 * np.log10(2.0)).abs()[above].max()) < 1e-4
+
+
+def test_predict_pipelined_host_path(K):
+    """predict() with host buffers (chunked H2D / kernels / D2H on three streams) == device call."""
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, size=(37, 9000, 2)).astype(np.float32)
+    layer = K.get_melspectrogram_layer(n_fft=512, hop_length=128, n_mels=40, return_decibel=True, db_dynamic_range=30.0)
+    full = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    for bs in (None, 5, 64):
+        np.testing.assert_array_equal(layer.predict(x, batch_size=bs), full)
+    pinned = torch.from_numpy(x).pin_memory()
+    np.testing.assert_array_equal(layer.predict(pinned), full)
