@@ -89,12 +89,13 @@ static inline void kb_make_fb_chunks(const float* fb, int n_freq, int n_bands, i
                     hi = k + 1;
                 }
             if (hi <= lo) { lo = 0; hi = 1; }
+            lo &= ~1;   // chunks start on even bins: the kernel loads bin pairs as aligned vectors
             for (int k0 = lo; k0 < hi; k0 += 4) {
                 kb_f4 w;
                 float* wp = &w.x;
                 for (int j = 0; j < 4; ++j) {
                     const int k = k0 + j;
-                    wp[j] = (k < hi && k < n_freq) ? fb[(size_t)k * n_bands + m] : 0.0f;
+                    wp[j] = (k < hi && k < n_freq) ? fb[(size_t)k * n_bands + m] : 0.0f;   // zero outside the band
                 }
                 kb_i2 mt;
                 mt.x = k0;

@@ -39,7 +39,7 @@ struct KbStftSmem {
 // distinct banks for distinct frame columns.
 KB_HD int kb_exw(int Q) {
     const int FPW = 32 / Q;
-    return 32 * 33 + (FPW >= 2 ? FPW / 2 : 1);
+    return 32 * 33 + FPW;   // region stride = 2112 + 2*FPW floats: the filterbank phase reads 2 bins x FPW frames per lane
 }
 
 // Shared-memory carve-up; used by the host launcher (size) and by the kernel (offsets).
@@ -253,6 +253,22 @@ KB_HD void kb_load_vec(float* dst, const float* src) {
         for (int j = 0; j < FPW / 4; ++j) {
             const kb_f4 v = reinterpret_cast<const kb_f4*>(src)[j];
             dst[4 * j] = v.x; dst[4 * j + 1] = v.y; dst[4 * j + 2] = v.z; dst[4 * j + 3] = v.w;
+        }
+    }
+}
+
+template <int FPW>
+KB_HD void kb_store_vec(float* dst, const float* src) {
+    if constexpr (FPW == 1) {
+        dst[0] = src[0];
+    } else if constexpr (FPW == 2) {
+        float2 v; v.x = src[0]; v.y = src[1];
+        *reinterpret_cast<float2*>(dst) = v;
+    } else {
+#pragma unroll
+        for (int j = 0; j < FPW / 4; ++j) {
+            kb_f4 v; v.x = src[4 * j]; v.y = src[4 * j + 1]; v.z = src[4 * j + 2]; v.w = src[4 * j + 3];
+            reinterpret_cast<kb_f4*>(dst)[j] = v;
         }
     }
 }
@@ -510,15 +526,26 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                     const float* magr = reinterpret_cast<const float*>(R.v);
                     float* mw = reinterpret_cast<float*>(ex_s + warp * EXS);
 #pragma unroll
-                    for (int gg = 0; gg < FPW; ++gg) {
+                    for (int i = 0; i < Q / 2; ++i) {
+                        const int k = lane + 32 * i;
+                        float lo[FPW], hi[FPW];
 #pragma unroll
-                        for (int i = 0; i < Q / 2; ++i) {
-                            const int k = lane + 32 * i;
-                            mw[k * FPW + gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 0];
-                            mw[(P - k) * FPW + gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 1];
+                        for (int gg = 0; gg < FPW; ++gg) {
+                            lo[gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 0];
+                            hi[gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 1];
                         }
-                        if (lane == 0) mw[(P / 2) * FPW + gg] = magr[(gg * (Q / 2 + 1) + Q / 2) * 2 + 0];
-                        if (lane < 3) mw[(P + 1 + lane) * FPW + gg] = 0.0f;   // pad bins read by padded bands
+                        kb_store_vec<FPW>(mw + k * FPW, lo);
+                        kb_store_vec<FPW>(mw + (P - k) * FPW, hi);
+                    }
+                    if (lane == 0) {
+                        float mid[FPW];
+#pragma unroll
+                        for (int gg = 0; gg < FPW; ++gg) mid[gg] = magr[(gg * (Q / 2 + 1) + Q / 2) * 2 + 0];
+                        kb_store_vec<FPW>(mw + (P / 2) * FPW, mid);
+                    }
+                    if (lane < 3) {
+#pragma unroll
+                        for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;   // pad bins
                     }
                 KB_PHASE_END
             }
@@ -552,17 +579,15 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                     const kb_f4 wv = cw_s[i];                             // 16 B, uniform within the group
                     const kb_i2 mt = cm_s[i];
                     const float* mp = mw + mt.x * FPW;
-                    float m0[FPW], m1[FPW], m2[FPW], m3[FPW];
-                    kb_load_vec<FPW>(m0, mp);
-                    kb_load_vec<FPW>(m1, mp + FPW);
-                    kb_load_vec<FPW>(m2, mp + 2 * FPW);
-                    kb_load_vec<FPW>(m3, mp + 3 * FPW);
+                    float m01[2 * FPW], m23[2 * FPW];          // bins (k, k+1) and (k+2, k+3), k even
+                    kb_load_vec<2 * FPW>(m01, mp);
+                    kb_load_vec<2 * FPW>(m23, mp + 2 * FPW);
 #pragma unroll
                     for (int g = 0; g < FPW; ++g) {
-                        a0[g] += wv.x * m0[g];
-                        a1[g] += wv.y * m1[g];
-                        a0[g] += wv.z * m2[g];
-                        a1[g] += wv.w * m3[g];
+                        a0[g] += wv.x * m01[g];
+                        a1[g] += wv.y * m01[FPW + g];
+                        a0[g] += wv.z * m23[g];
+                        a1[g] += wv.w * m23[FPW + g];
                     }
                     if (mt.y >= 0) {
 #pragma unroll
