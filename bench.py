@@ -229,10 +229,12 @@ def main():
     _native.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
+    t_host0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         outs[i % N_SETS] = layer(xs[i % N_SETS])
     e1.record()
+    host_submit_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     barrier()
     sampler.stop()
     _native.profile_enable(False)
@@ -299,7 +301,7 @@ def main():
                    'parallelism': 'dp%d (batch sharded, no collective in the data path)' % world,
                    'l2': '%d rotating input/output sets (%.0f MB) > 126 MB L2' % (
                        N_SETS, N_SETS * algorithmic_bytes_per_step() / 1e6),
-                   'launch': _native.last_launch_info()},
+                   'launch': _native.last_launch_info(), 'host_submit_ms_per_step': host_submit_ms},
         'roofline': roofline,
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

@@ -97,21 +97,30 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_idft_kernel(const __grid
 
 // Dynamic-range clamp, kapre/backend.py:190-192: y = max(y, max_item(y) - dynamic_range).
 // item_max holds max(x, amin) per item (uint view); log is monotone, so the item maximum in
-// dB is dB(item_max).  Exits immediately when the clamp cannot bind (threshold <= dB(amin)),
-// which is the common case, so no output byte is re-read.
-__global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size, int chunks,
-                                   const unsigned int* __restrict__ item_max, float amin,
+// dB is dB(item_max).  One CTA per item: it reads the maximum, RESETS it to zero (the workspace
+// is self-cleaning: zero before the first use, zero again after every call) and returns
+// immediately when the clamp cannot bind (threshold <= dB(amin)), which is the common case
+// (SURVEY section 7), so no output byte is re-read.  Launched with programmatic dependent
+// launch: the grid is scheduled while the producer kernel drains.
+__global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size,
+                                   unsigned int* __restrict__ item_max, float amin,
                                    float db_mul, float db_sub, float dyn_range) {
-    const long long item = blockIdx.x / chunks;
-    const int chunk = blockIdx.x - (int)(item * chunks);
-    const float mx = __uint_as_float(item_max[item]);
+#if __CUDA_ARCH__ >= 900
+    cudaGridDependencySynchronize();
+#endif
+    const long long item = blockIdx.x;
+    __shared__ unsigned int s_mx;
+    if (threadIdx.x == 0) {
+        s_mx = item_max[item];
+        item_max[item] = 0u;
+    }
+    __syncthreads();
+    const float mx = __uint_as_float(s_mx);
     const float thr = (db_mul * __log2f(fmaxf(mx, amin)) - db_sub) - dyn_range;
     const float floor_db = db_mul * __log2f(amin) - db_sub;
     if (!(thr > floor_db)) return;
     float* yi = y + item * item_size;
-    for (long long i = (long long)chunk * blockDim.x + threadIdx.x; i < item_size;
-         i += (long long)chunks * blockDim.x)
-        yi[i] = fmaxf(yi[i], thr);
+    for (long long i = threadIdx.x; i < item_size; i += blockDim.x) yi[i] = fmaxf(yi[i], thr);
 }
 
 // Stand-alone MagnitudeToDecibel pass 1: y = db(max(x, amin)), per-item max of max(x, amin).
@@ -307,16 +316,21 @@ static int kb_check_device(const DevInfo& d) {
     return 0;
 }
 
-static int kb_launch_clamp(float* y, long long n_items, long long item_size, const unsigned int* item_max,
+static int kb_launch_clamp(float* y, long long n_items, long long item_size, unsigned int* item_max,
                            float amin, float db_mul, float db_sub, float dr, cudaStream_t st) {
     if (n_items <= 0 || item_size <= 0) return 0;
-    long long chunks = (item_size + 256 * 8 - 1) / (256 * 8);
-    if (chunks > 64) chunks = 64;
-    if (chunks < 1) chunks = 1;
-    const long long grid = n_items * chunks;
-    if (grid > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items for the clamp kernel");
-    kb_db_clamp_kernel<<<(unsigned)grid, 256, 0, st>>>(y, item_size, (int)chunks, item_max, amin, db_mul, db_sub, dr);
-    KB_CUDA(cudaGetLastError());
+    if (n_items > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items for the clamp kernel");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_items);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = kb_env_int("KAPRE_B200_PDL", 1) ? 1 : 0;
+    KB_CUDA(cudaLaunchKernelEx(&cfg, kb_db_clamp_kernel, y, item_size, item_max, amin, db_mul, db_sub, dr));
     g_launches++;
     return 0;
 }
@@ -510,7 +524,6 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
     long long gmax = (long long)plan->dev.sm_count * cfg.bps;
     const int grid = (int)(tiles < gmax ? tiles : gmax);
-    if (dbmode) KB_CUDA(cudaMemsetAsync(workspace_dev, 0, (size_t)B * 4, st));
     switch (plan->Q) {
         case 4: rc = kb_launch_stft<4>(p, grid, cfg.smem, st); break;
         case 8: rc = kb_launch_stft<8>(p, grid, cfg.smem, st); break;
@@ -532,7 +545,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         if (od->stride_b != item_size)
             return kb_fail(KAPRE_E_UNSUPPORTED, "decibel modes need a batch-contiguous output (stride_b=%lld, item=%lld)",
                            (long long)od->stride_b, item_size);
-        rc = kb_launch_clamp((float*)out_dev, B, item_size, (const unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
+        rc = kb_launch_clamp((float*)out_dev, B, item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
                              db->dynamic_range, st);
     }
     return rc;
@@ -758,12 +771,11 @@ int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_ite
     if (chunks < 1) chunks = 1;
     const long long grid = n_items * chunks;
     if (grid > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items");
-    KB_CUDA(cudaMemsetAsync(workspace_dev, 0, (size_t)n_items * 4, st));
     kb_db_kernel<<<(unsigned)grid, 256, 0, st>>>(x_dev, out_dev, item_size, (int)chunks, (unsigned int*)workspace_dev,
                                                  db->amin, db_mul, db_sub);
     KB_CUDA(cudaGetLastError());
     g_launches++;
-    return kb_launch_clamp(out_dev, n_items, item_size, (const unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
+    return kb_launch_clamp(out_dev, n_items, item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
                            db->dynamic_range, st);
 }
 

@@ -58,8 +58,20 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     return host.numpy()
 
 
+_ws_cache = {}
+
+
 def _workspace(n_items: int, device) -> torch.Tensor:
-    return torch.empty(max(int(n_items), 1), dtype=torch.int32, device=device)
+    """Per-(device, stream) zero-initialised scratch for the per-item dB maxima.  The kernels leave
+    it zeroed (self-cleaning contract of the C ABI), so it is allocated and cleared only once."""
+    n = max(int(n_items), 1)
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.zeros(max(n, 1024), dtype=torch.int32, device=device)
+        _ws_cache[key] = ws
+    return ws
 
 
 class _Handle:
