@@ -46,7 +46,10 @@ enum {
     KAPRE_OUT_MAG = 1,     /* float32     STFT -> Magnitude                  time_frequency.py:351-359 */
     KAPRE_OUT_MAG_DB = 2,  /* float32     STFT -> Magnitude -> MagnitudeToDecibel      composed.py:32-135 */
     KAPRE_OUT_FB = 3,      /* float32     STFT -> Magnitude -> ApplyFilterbank         composed.py:138-261 */
-    KAPRE_OUT_FB_DB = 4    /* float32     ... -> ApplyFilterbank -> MagnitudeToDecibel composed.py:254-261 */
+    KAPRE_OUT_FB_DB = 4,   /* float32     ... -> ApplyFilterbank -> MagnitudeToDecibel composed.py:254-261 */
+    KAPRE_OUT_MAG_PHASE = 5 /* float32    get_stft_mag_phase (composed.py:420-511): the output tensor has 2*channels
+                             *             channels, magnitudes (dB-scaled if `db` is given) in channels [0, C) and
+                             *             tf.math.angle phases in channels [C, 2C) */
 };
 
 /* Waveform tensor: element strides of (batch, channel, sample). */

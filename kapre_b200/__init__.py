@@ -23,6 +23,7 @@ from .composed import (  # noqa: E402
     get_melspectrogram_layer,
     get_log_frequency_spectrogram_layer,
     get_perfectly_reconstructing_stft_istft,
+    get_stft_mag_phase,
 )
 
 __all__ = [
@@ -30,5 +31,5 @@ __all__ = [
     'STFT', 'InverseSTFT', 'Magnitude', 'Phase', 'MagnitudeToDecibel', 'ApplyFilterbank',
     'Layer', 'Sequential',
     'get_stft_magnitude_layer', 'get_melspectrogram_layer', 'get_log_frequency_spectrogram_layer',
-    'get_perfectly_reconstructing_stft_istft',
+    'get_perfectly_reconstructing_stft_istft', 'get_stft_mag_phase',
 ]

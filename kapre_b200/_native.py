@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_lib', 'libkapre_b200.so')
 
-OUT_COMPLEX, OUT_MAG, OUT_MAG_DB, OUT_FB, OUT_FB_DB = range(5)
+OUT_COMPLEX, OUT_MAG, OUT_MAG_DB, OUT_FB, OUT_FB_DB, OUT_MAG_PHASE = range(6)
 
 
 class KapreNativeError(RuntimeError):

@@ -18,8 +18,8 @@ from .backend import _CH_DEFAULT_STR, _CH_FIRST_STR, _CH_LAST_STR
 from .time_frequency import (STFT, ApplyFilterbank, InverseSTFT, Layer, Magnitude, MagnitudeToDecibel, Phase,
                              get_registered_object)
 
-__all__ = ['Sequential', 'get_stft_magnitude_layer', 'get_melspectrogram_layer',
-           'get_log_frequency_spectrogram_layer', 'get_perfectly_reconstructing_stft_istft']
+__all__ = ['Sequential', 'StftMagPhase', 'get_stft_magnitude_layer', 'get_melspectrogram_layer',
+           'get_log_frequency_spectrogram_layer', 'get_perfectly_reconstructing_stft_istft', 'get_stft_mag_phase']
 
 
 _streams = {}
@@ -229,3 +229,55 @@ def get_perfectly_reconstructing_stft_istft(n_fft, hop_length, waveform_data_for
                         input_data_format=stft_data_format, output_data_format=waveform_data_format,
                         name=istft_name)
     return stft, istft
+
+
+class StftMagPhase(Layer):
+    """The functional model built by ``get_stft_mag_phase`` (kapre/composed.py:478-511): STFT, then
+    Magnitude (optionally MagnitudeToDecibel) and Phase, concatenated on the channel axis.  On the
+    fused path all of it is one kernel launch writing both halves of the output tensor."""
+
+    def __init__(self, stft, magnitude, phase, mag_to_decibel, ch_axis, name=None):
+        super().__init__(name=name)
+        self.stft, self.magnitude, self.phase, self.mag_to_decibel = stft, magnitude, phase, mag_to_decibel
+        self.ch_axis = ch_axis
+        self.layers = [stft, magnitude, phase] + ([mag_to_decibel] if mag_to_decibel is not None else [])
+
+    def call(self, x):
+        stft, db = self.stft, self.mag_to_decibel
+        natural_axis = 1 if stft.output_data_format == _CH_FIRST_STR else 3
+        if x.dim() == 3 and self.ch_axis == natural_axis and stft.plan.supports_mode(N.OUT_MAG_PHASE):
+            dbt = None
+            if db is not None:
+                for nm in ('ref_value', 'amin', 'dynamic_range'):   # kapre/backend.py:168-173
+                    if getattr(db, nm) <= 0:
+                        raise ValueError('%s must be positive, got: %s' % (nm, getattr(db, nm)))
+                dbt = (db.ref_value, db.amin, db.dynamic_range)
+            return ops.stft_forward(x, stft.plan, stft.input_data_format, stft.output_data_format, stft.pad_begin,
+                                    stft.pad_end, N.OUT_MAG_PHASE, None, dbt)
+        s = stft.call(x)
+        mag = self.magnitude.call(s)
+        ph = self.phase.call(s)
+        if db is not None:
+            mag = db.call(mag)
+        return torch.cat([mag, ph], dim=self.ch_axis)
+
+    def predict(self, x, batch_size=None, verbose=0, **kwargs):
+        y = self(x)
+        return ops.to_host(y) if isinstance(y, torch.Tensor) else y
+
+
+def get_stft_mag_phase(input_shape, n_fft=2048, win_length=None, hop_length=None, window_name=None, pad_begin=False,
+                       pad_end=False, return_decibel=False, db_amin=1e-5, db_ref_value=1.0, db_dynamic_range=80.0,
+                       input_data_format='default', output_data_format='default', name='stft_mag_phase'):
+    """Magnitude and phase of the STFT side by side on the channel axis -- kapre/composed.py:420-511.
+    Output ``(batch, time, freq, 2*ch)`` / ``(batch, 2*ch, time, freq)``: ``[ch magnitude; ch phase]``.
+    ``input_shape`` is accepted for signature compatibility (the reference needs it for ``keras.Input``)."""
+    backend.validate_data_format_str(input_data_format)
+    backend.validate_data_format_str(output_data_format)
+    waveform_to_stft = STFT(n_fft=n_fft, win_length=win_length, hop_length=hop_length, window_name=window_name,
+                            pad_begin=pad_begin, pad_end=pad_end, input_data_format=input_data_format,
+                            output_data_format=output_data_format)
+    mag_to_decibel = MagnitudeToDecibel(ref_value=db_ref_value, amin=db_amin, dynamic_range=db_dynamic_range) \
+        if return_decibel else None
+    ch_axis = 1 if output_data_format == _CH_FIRST_STR else 3     # sic: the unresolved string, composed.py:504
+    return StftMagPhase(waveform_to_stft, Magnitude(), Phase(), mag_to_decibel, ch_axis, name=name)

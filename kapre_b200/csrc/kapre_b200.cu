@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_idft_kernel(const __grid
 // immediately when the clamp cannot bind (threshold <= dB(amin)), which is the common case
 // (SURVEY section 7), so no output byte is re-read.  Launched with programmatic dependent
 // launch: the grid is scheduled while the producer kernel drains.
-__global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size,
+__global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size, long long run, long long period,
                                    unsigned int* __restrict__ item_max, float amin,
                                    float db_mul, float db_sub, float dyn_range) {
 #if __CUDA_ARCH__ >= 900
@@ -120,7 +120,13 @@ __global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size,
     const float floor_db = db_mul * __log2f(amin) - db_sub;
     if (!(thr > floor_db)) return;
     float* yi = y + item * item_size;
-    for (long long i = threadIdx.x; i < item_size; i += blockDim.x) yi[i] = fmaxf(yi[i], thr);
+    // only elements with (i mod period) < run are decibel values (magnitude half of a mag+phase tensor)
+    if (run >= period) {
+        for (long long i = threadIdx.x; i < item_size; i += blockDim.x) yi[i] = fmaxf(yi[i], thr);
+    } else {
+        for (long long i = threadIdx.x; i < item_size; i += blockDim.x)
+            if (i % period < run) yi[i] = fmaxf(yi[i], thr);
+    }
 }
 
 // Stand-alone MagnitudeToDecibel pass 1: y = db(max(x, amin)), per-item max of max(x, amin).
@@ -293,6 +299,7 @@ static int kb_launch_stft(const KbStftParams& p, int grid, int smem, cudaStream_
         case KB_OUT_MAG_DB: return kb_launch_stft_qm<Q, KB_OUT_MAG_DB>(p, grid, smem, st);
         case KB_OUT_FB: return kb_launch_stft_qm<Q, KB_OUT_FB>(p, grid, smem, st);
         case KB_OUT_FB_DB: return kb_launch_stft_qm<Q, KB_OUT_FB_DB>(p, grid, smem, st);
+        case KB_OUT_MAG_PHASE: return kb_launch_stft_qm<Q, KB_OUT_MAG_PHASE>(p, grid, smem, st);
     }
     return kb_fail(KAPRE_E_INVALID, "bad mode");
 }
@@ -317,7 +324,8 @@ static int kb_check_device(const DevInfo& d) {
 }
 
 static int kb_launch_clamp(float* y, long long n_items, long long item_size, unsigned int* item_max,
-                           float amin, float db_mul, float db_sub, float dr, cudaStream_t st) {
+                           float amin, float db_mul, float db_sub, float dr, cudaStream_t st,
+                           long long run = 1, long long period = 1) {
     if (n_items <= 0 || item_size <= 0) return 0;
     if (n_items > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items for the clamp kernel");
     cudaLaunchConfig_t cfg{};
@@ -330,7 +338,7 @@ static int kb_launch_clamp(float* y, long long n_items, long long item_size, uns
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = kb_env_int("KAPRE_B200_PDL", 1) ? 1 : 0;
-    KB_CUDA(cudaLaunchKernelEx(&cfg, kb_db_clamp_kernel, y, item_size, item_max, amin, db_mul, db_sub, dr));
+    KB_CUDA(cudaLaunchKernelEx(&cfg, kb_db_clamp_kernel, y, item_size, run, period, item_max, amin, db_mul, db_sub, dr));
     g_launches++;
     return 0;
 }
@@ -439,7 +447,7 @@ int kapre_stft_num_frames(const kapre_stft_plan* p, int length, int pad_begin, i
 
 int kapre_stft_supports_mode(const kapre_stft_plan* p, int mode) {
     if (!p) return 0;
-    if (mode < KAPRE_OUT_COMPLEX || mode > KAPRE_OUT_FB_DB) return 0;
+    if (mode < KAPRE_OUT_COMPLEX || mode > KAPRE_OUT_MAG_PHASE) return 0;
     if (p->Q) return 1;
     return mode == KAPRE_OUT_COMPLEX || mode == KAPRE_OUT_MAG;
 }
@@ -448,7 +456,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
                        int pad_begin, int pad_end, int mode, void* out_dev, const kapre_spec_desc* od,
                        const kapre_filterbank* fb, const kapre_db_cfg* db, void* workspace_dev, void* stream) {
     if (!plan || !xd || !od) return kb_fail(KAPRE_E_INVALID, "null argument");
-    if (mode < KAPRE_OUT_COMPLEX || mode > KAPRE_OUT_FB_DB) return kb_fail(KAPRE_E_INVALID, "bad mode %d", mode);
+    if (mode < KAPRE_OUT_COMPLEX || mode > KAPRE_OUT_MAG_PHASE) return kb_fail(KAPRE_E_INVALID, "bad mode %d", mode);
     int rc = kb_check_device(plan->dev);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -460,7 +468,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if ((long long)T * plan->hop + plan->n_fft > 0x7fffffffLL)
         return kb_fail(KAPRE_E_UNSUPPORTED, "signal too long");
     const bool fbmode = (mode == KAPRE_OUT_FB || mode == KAPRE_OUT_FB_DB);
-    const bool dbmode = (mode == KAPRE_OUT_MAG_DB || mode == KAPRE_OUT_FB_DB);
+    const bool dbmode = (mode == KAPRE_OUT_MAG_DB || mode == KAPRE_OUT_FB_DB || (mode == KAPRE_OUT_MAG_PHASE && db != nullptr));
     if (fbmode) {
         if (!fb) return kb_fail(KAPRE_E_INVALID, "filterbank required for mode %d", mode);
         if (fb->n_freq != plan->n_fft / 2 + 1)
@@ -519,6 +527,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         p.cw = fb->cw; p.cm = fb->cm; p.cg = fb->cg; p.n_chunks = fb->n_chunks;
     }
     if (dbmode) { p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev; }
+    if (mode == KAPRE_OUT_MAG_PHASE) { p.db_on = dbmode ? 1 : 0; p.ph_off = (long long)C * od->stride_c; }
     p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
     const long long tiles = (long long)B * C * p.n_tiles_t;
     if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
@@ -541,12 +550,19 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if (dbmode) {
         // items are contiguous blocks of stride_b elements in both data formats
         const long long K = fbmode ? fb->n_bands : (plan->n_fft / 2 + 1);
-        const long long item_size = (long long)C * T * K;
+        const long long chans = (mode == KAPRE_OUT_MAG_PHASE) ? 2LL * C : C;
+        const long long item_size = chans * T * K;
         if (od->stride_b != item_size)
             return kb_fail(KAPRE_E_UNSUPPORTED, "decibel modes need a batch-contiguous output (stride_b=%lld, item=%lld)",
                            (long long)od->stride_b, item_size);
+        long long run = 1, period = 1;
+        if (mode == KAPRE_OUT_MAG_PHASE) {   // clamp only the magnitude channels [0, C) of the 2C-channel item
+            if (od->stride_c == 1 && od->stride_f == chans && od->stride_t == K * chans) { run = C; period = chans; }
+            else if (od->stride_f == 1 && od->stride_t == K && od->stride_c == (long long)T * K) { run = (long long)C * T * K; period = item_size; }
+            else return kb_fail(KAPRE_E_UNSUPPORTED, "mag+phase decibel output must be a contiguous channels_first or channels_last tensor");
+        }
         rc = kb_launch_clamp((float*)out_dev, B, item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
-                             db->dynamic_range, st);
+                             db->dynamic_range, st, run, period);
     }
     return rc;
 }

@@ -32,6 +32,7 @@ enum KbMode {
     KB_OUT_MAG_DB = 2,   // dB(|STFT|), unclamped     (... -> MagnitudeToDecibel)
     KB_OUT_FB = 3,       // filterbank(|STFT|)        (... -> ApplyFilterbank)
     KB_OUT_FB_DB = 4,    // dB(filterbank(|STFT|))    (get_melspectrogram_layer(return_decibel))
+    KB_OUT_MAG_PHASE = 5,  // |STFT| (or its dB) and angle(STFT) side by side   (get_stft_mag_phase)
 };
 
 // Filterbank in "banded" form: band m covers bins [lo, hi) with weights w[off + (k - lo)];
@@ -77,6 +78,8 @@ struct KbStftParams {
     int n_chunks;
     // decibel (modes *_DB): y = db_mul * log2(max(v, amin)) - db_sub; per-item max of max(v, amin)
     float amin, db_mul, db_sub;
+    int db_on;               // KB_OUT_MAG_PHASE only: 1 = the magnitude half is decibel-scaled
+    long long ph_off;        // KB_OUT_MAG_PHASE only: element offset from a magnitude to its phase
     unsigned int* item_max;  // B entries, uint view of non-negative floats, zero-initialised
     // tiling
     int TF;          // frames per tile

@@ -81,6 +81,7 @@ struct KbThreadRegs {
 #define KB_SYNC_CTA
 static inline float kb_sqrt(float v) { return std::sqrt(v); }
 static inline float kb_log2(float v) { return std::log2(v); }
+static inline float kb_atan2(float y, float x) { return std::atan2(y, x); }
 static inline float kb_ldg(const float* p) { return *p; }
 static inline void kb_atomic_max_u32(unsigned int* p, unsigned int v) { if (v > *p) *p = v; }
 static inline unsigned int kb_f2u(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
@@ -96,6 +97,7 @@ static inline void kb_bar_wait(KbBar*, unsigned) {}
 #define KB_SYNC_CTA __syncthreads()
 KB_D float kb_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 KB_D float kb_log2(float v) { return __log2f(v); }
+KB_D float kb_atan2(float y, float x) { return atan2f(y, x); }
 KB_D float kb_ldg(const float* p) { return __ldg(p); }
 KB_D void kb_atomic_max_u32(unsigned int* p, unsigned int v) { atomicMax(p, v); }
 KB_D unsigned int kb_f2u(float f) { return __float_as_uint(f); }
@@ -287,6 +289,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     constexpr int EXW = 32 * 33;     // complex elements per warp in the exchange buffer
     constexpr bool fbmode = (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB);
     constexpr bool dbmode = (MODE == KB_OUT_MAG_DB || MODE == KB_OUT_FB_DB);
+    const bool dbany = dbmode || (MODE == KB_OUT_MAG_PHASE && p.db_on);   // per-item maximum needed
     const int NW = p.n_warps;
     const int kb_nt = NW * 32;
     (void)kb_nt;
@@ -498,7 +501,11 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                                 magr[(gg * (Q / 2 + 1) + i) * 2 + 0] = m1;
                                 magr[(gg * (Q / 2 + 1) + i) * 2 + 1] = m2;
                             } else if (valid) {
-                                if (dbmode) {
+                                if (MODE == KB_OUT_MAG_PHASE) {   // tf.math.angle, kapre/time_frequency.py:402
+                                    orl[(long long)k * sk + p.ph_off] = kb_atan2(X1.im, X1.re);
+                                    if (kk >= 0) orl[(long long)kk * sk + p.ph_off] = kb_atan2(-X2.im, X2.re);
+                                }
+                                if (dbany) {
                                     m1 = fmaxf(m1, p.amin);
                                     m2 = fmaxf(m2, p.amin);
                                     R.runmax = fmaxf(R.runmax, m1);
@@ -632,7 +639,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         }
 
         // ---- per-item maximum for the decibel clamp (kapre/backend.py:190-192) --------------
-        if (dbmode) {
+        if (dbany) {
 #if defined(KB_HOST_EMU)
             for (int tid = 0; tid < kb_nt; ++tid)
                 kb_atomic_max_u32(p.item_max + b, kb_f2u(kb_regs[tid].runmax));

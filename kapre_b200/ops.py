@@ -218,9 +218,10 @@ def stft_forward(x: torch.Tensor, plan: StftPlan, input_data_format, output_data
     fbmode = mode in (N.OUT_FB, N.OUT_FB_DB)
     K = fb.n_bands if fbmode else plan.n_fft // 2 + 1
     dtype = torch.complex64 if mode == N.OUT_COMPLEX else torch.float32
-    out, od = _spec_alloc(B, C, T, K, output_data_format, dtype, x.device)
+    c_out = 2 * C if mode == N.OUT_MAG_PHASE else C   # mag+phase: phases in channels [C, 2C)
+    out, od = _spec_alloc(B, c_out, T, K, output_data_format, dtype, x.device)
     dbc, ws = None, None
-    if mode in (N.OUT_MAG_DB, N.OUT_FB_DB):
+    if mode in (N.OUT_MAG_DB, N.OUT_FB_DB) or (mode == N.OUT_MAG_PHASE and db is not None):
         dbc = N.DbCfg(float(db[0]), float(db[1]), float(db[2]))
         ws = _workspace(B, x.device)
     if out.numel() == 0:

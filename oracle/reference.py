@@ -19,7 +19,7 @@ __all__ = [
     'frame_signal', 'stft_frames', 'stft_by_dft_matrix', 'stft_layer', 'magnitude',
     'hz_to_mel', 'mel_to_hz', 'filterbank_mel', 'filterbank_log', 'apply_filterbank',
     'magnitude_to_decibel', 'inverse_stft_window', 'inverse_stft_frames', 'istft_layer',
-    'melspectrogram_layer', 'stft_magnitude_layer',
+    'melspectrogram_layer', 'stft_magnitude_layer', 'phase', 'stft_mag_phase_layer',
 ]
 
 CH_FIRST = 'channels_first'
@@ -341,3 +341,25 @@ def melspectrogram_layer(x, n_fft=2048, win_length=None, hop_length=None, window
     if return_decibel:
         s = magnitude_to_decibel(s, db_ref_value, db_amin, db_dynamic_range)
     return s
+
+
+def phase(x):
+    """kapre.Phase.call with approx_atan_accuracy=None, kapre/time_frequency.py:391-402 (tf.math.angle)."""
+    return np.angle(x)
+
+
+def stft_mag_phase_layer(x, n_fft=2048, win_length=None, hop_length=None, window_name=None, pad_begin=False,
+                         pad_end=False, return_decibel=False, db_amin=1e-5, db_ref_value=1.0,
+                         db_dynamic_range=80.0, input_data_format='default', output_data_format='default',
+                         dtype=np.float64):
+    """kapre.composed.get_stft_mag_phase, kapre/composed.py:420-511: magnitude (optionally dB) and
+    phase concatenated on the channel axis (1 for 'channels_first', else 3 -- note the reference
+    compares the *unresolved* string at :504, so 'default' concatenates on axis 3 = channels_last)."""
+    s = stft_layer(x, n_fft, win_length, hop_length, window_name, pad_begin, pad_end, input_data_format,
+                   output_data_format, dtype=dtype)
+    mag = magnitude(s)
+    ph = phase(s)
+    if return_decibel:
+        mag = magnitude_to_decibel(mag, db_ref_value, db_amin, db_dynamic_range)
+    ch_axis = 1 if output_data_format == CH_FIRST else 3
+    return np.concatenate([mag, ph.astype(mag.dtype)], axis=ch_axis)

@@ -28,6 +28,7 @@ static void run_stft(const KbStftParams& p, int n_cta) {
         case KB_OUT_MAG_DB: run_stft_qm<Q, KB_OUT_MAG_DB>(p, n_cta); break;
         case KB_OUT_FB: run_stft_qm<Q, KB_OUT_FB>(p, n_cta); break;
         case KB_OUT_FB_DB: run_stft_qm<Q, KB_OUT_FB_DB>(p, n_cta); break;
+        case KB_OUT_MAG_PHASE: run_stft_qm<Q, KB_OUT_MAG_PHASE>(p, n_cta); break;
     }
 }
 
@@ -47,7 +48,8 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
                 int n_fft, int win_length, int hop, int pad_left, int T, const float* window,
                 int mode, void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk,
                 const float* fb, int n_freq, int n_bands, float amin, float db_mul, float db_sub,
-                unsigned int* item_max, int TF, int n_warps, int n_cta, int dbuf, int bulk, long long x_numel) {
+                unsigned int* item_max, int TF, int n_warps, int n_cta, int dbuf, int bulk, long long x_numel,
+                int db_on, long long ph_off) {
     const int Q = kb_q_for_nfft(n_fft);
     if (!Q) return -1;
     if ((mode == KB_OUT_FB || mode == KB_OUT_FB_DB) && TF != n_warps * (32 / Q)) return -2;  // kernel contract
@@ -71,7 +73,7 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     if (fb) { p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
     p.x_lo = x; p.x_hi = x + x_numel; p.x_numel = x_numel; p.x_align = (unsigned)(((uintptr_t)x >> 2) & 3);
     p.bulk_ok = (bulk && x_sl == 1) ? 1 : 0; p.dbuf = dbuf;
-    p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max;
+    p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max; p.db_on = db_on; p.ph_off = ph_off;
     p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
     switch (Q) {
         case 4: run_stft<4>(p, n_cta); break;

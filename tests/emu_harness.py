@@ -14,7 +14,7 @@ _SRC = os.path.join(_HERE, 'emu', 'kb_emu.cpp')
 _OUT = os.path.join(_HERE, 'emu', '_build', 'libkb_emu.so')
 _CSRC = os.path.join(_HERE, '..', 'kapre_b200', 'csrc')
 
-MODE_COMPLEX, MODE_MAG, MODE_MAG_DB, MODE_FB, MODE_FB_DB = range(5)
+MODE_COMPLEX, MODE_MAG, MODE_MAG_DB, MODE_FB, MODE_FB_DB, MODE_MAG_PHASE = range(6)
 
 
 def _needs_build():
@@ -38,7 +38,7 @@ def _fp(a):
 
 
 def emu_stft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, out_fmt,
-             fb=None, amin=1e-5, ref=1.0, TF=16, n_warps=4, n_cta=3, dbuf=1, bulk=1):
+             fb=None, amin=1e-5, ref=1.0, TF=16, n_warps=4, n_cta=3, dbuf=1, bulk=1, db_on=0):
     """x: (B, L, C) channels_last or (B, C, L) channels_first float32.  Returns (out, item_max)."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -54,12 +54,13 @@ def emu_stft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt
     F = n_fft // 2 + 1
     K = fb.shape[1] if mode in (MODE_FB, MODE_FB_DB) else F
     dt = np.complex64 if mode == MODE_COMPLEX else np.float32
+    Co = 2 * C if mode == MODE_MAG_PHASE else C   # mag+phase: phases live in channels [C, 2C)
     if out_fmt == 'channels_last':
-        out = np.full((B, T, K, C), np.nan, dtype=dt)
-        osb, ost, osk, osc = T * K * C, K * C, C, 1
+        out = np.full((B, T, K, Co), np.nan, dtype=dt)
+        osb, ost, osk, osc = T * K * Co, K * Co, Co, 1
     else:
-        out = np.full((B, C, T, K), np.nan, dtype=dt)
-        osb, osc, ost, osk = C * T * K, T * K, K, 1
+        out = np.full((B, Co, T, K), np.nan, dtype=dt)
+        osb, osc, ost, osk = Co * T * K, T * K, K, 1
     item_max = np.zeros(B, dtype=np.uint32)
     window = np.ascontiguousarray(window, dtype=np.float32)
     fbp, nfreq, nb = None, 0, 0
@@ -72,7 +73,8 @@ def emu_stft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt
     rc = lib.kb_emu_stft(_fp(x), LL(sb), LL(sc), LL(sl), B, C, L, n_fft, win_length, hop, pad_left, T,
                          _fp(window), mode, _fp(out), LL(osb), LL(osc), LL(ost), LL(osk),
                          fbp, nfreq, nb, ctypes.c_float(amin), ctypes.c_float(db_mul),
-                         ctypes.c_float(db_sub), _fp(item_max), TF, n_warps, n_cta, dbuf, bulk, LL(x.size))
+                         ctypes.c_float(db_sub), _fp(item_max), TF, n_warps, n_cta, dbuf, bulk, LL(x.size),
+                         db_on, LL(C * osc))
     assert rc == 0
     return out, item_max.view(np.float32)
 

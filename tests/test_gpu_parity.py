@@ -404,3 +404,42 @@ def test_predict_pipelined_host_path(K):
         np.testing.assert_array_equal(layer.predict(x, batch_size=bs), full)
     pinned = torch.from_numpy(x).pin_memory()
     np.testing.assert_array_equal(layer.predict(pinned), full)
+
+
+# ------------------------------------------------------------------------------- "next" row: get_stft_mag_phase
+@pytest.mark.parametrize('fmt', ['default', 'channels_first', 'channels_last'])
+@pytest.mark.parametrize('n_fft,hop', [(512, 256), (2048, 512), (1000, 250)])
+@pytest.mark.parametrize('db', [False, True])
+def test_stft_mag_phase(K, golden, fmt, n_fft, hop, db):
+    """Mirror of tests/test_time_frequency.py:390-444 (magnitude atol 2e-4) plus the phase half,
+    which the reference leaves untested, against the oracle (kapre/composed.py:420-511)."""
+    rng = np.random.default_rng(n_fft)
+    C = 2
+    x = rng.uniform(-1, 1, size=(3, C, 7000) if fmt == 'channels_first' else (3, 7000, C)).astype(np.float32)
+    x[1] *= 1e-2
+    kw = dict(n_fft=n_fft, hop_length=hop, return_decibel=db, db_dynamic_range=40.0, input_data_format=fmt,
+              output_data_format=fmt)
+    layer = K.get_stft_mag_phase(input_shape=x.shape[1:], **kw)
+    got = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.stft_mag_phase_layer(x, **kw)
+    assert got.shape == ref.shape
+    ax = 1 if fmt == 'channels_first' else 3
+    gm, gp = np.split(got, 2, axis=ax)
+    rm, rp = np.split(ref, 2, axis=ax)
+    lin = np.abs(O.stft_layer(x, n_fft, None, hop, input_data_format=fmt, output_data_format=fmt))
+    sig = lin > 1e-3 * lin.reshape(3, -1).max(1).reshape(3, 1, 1, 1)
+    if db:
+        assert np.abs(gm - rm)[sig].max() < 2e-3          # dB
+        assert np.abs(gm - rm).max() < 5e-2               # incl. clamp-floor region (fp32 noise bins)
+    else:
+        np.testing.assert_allclose(gm, rm, atol=2e-4)     # reference tolerance
+    d = np.angle(np.exp(1j * (gp - rp)))
+    assert np.abs(d)[sig].max() < 2e-4                    # radians, where the bin is not rounding noise
+    # speech fixture, magnitude half only (what the reference test checks)
+    xs = golden['audio'][None, :, None] if fmt != 'channels_first' else golden['audio'][None, None, :]
+    g2 = K.get_stft_mag_phase(input_shape=xs.shape[1:], n_fft=512, win_length=512, hop_length=256,
+                              input_data_format=fmt, output_data_format=fmt)(xs)
+    mag = np.take(g2[0], [0], axis=0 if fmt == 'channels_first' else 2)
+    refm = np.abs(golden['stft_512_256_hann_window'])
+    refm = refm[None] if fmt == 'channels_first' else refm[:, :, None]
+    np.testing.assert_allclose(mag, refm, atol=2e-4)
