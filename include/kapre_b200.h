@@ -131,6 +131,20 @@ int kapre_phase(const void* x_complex_dev, float* out_dev, int64_t n, void* stre
 int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_items, int64_t item_size,
                                const kapre_db_cfg* db, void* workspace_dev, void* stream);
 
+/* ---- adjacent layers (SURVEY 8f "next" rows) ------------------------------------------------ */
+/* kapre.Delta (kapre/time_frequency.py:563-644): y[t] = sum_{m=-n..n} m * x[t+m] / (2 sum m^2) along the
+ * time axis of a contiguous tensor viewed as (outer, frames, inner); x is extended beyond its ends by
+ * `pad_mode` (0 = symmetric, 1 = reflect, 2 = constant zero -- tf.pad's modes).  win_length = 2n+1. */
+int kapre_delta(const float* x_dev, float* out_dev, int64_t outer, int64_t frames, int64_t inner,
+                int win_length, int pad_mode, void* stream);
+/* kapre.Frame (kapre/signal.py:22-119, tf.signal.frame): out[b, c, t, n] = x[b, c, t*hop + n], or
+ * pad_value beyond the signal when pad_end.  out_desc strides are (batch, channel, frame, sample-in-frame). */
+int kapre_frame(const float* x_dev, const kapre_wave_desc* x_desc, int frame_length, int hop_length, int pad_end,
+                float pad_value, float* out_dev, const kapre_spec_desc* out_desc, void* stream);
+/* kapre.Energy (kapre/signal.py:123-233): scale * sum_n frame[n]^2 per frame; out_desc.length = frames. */
+int kapre_energy(const float* x_dev, const kapre_wave_desc* x_desc, int frame_length, int hop_length, int pad_end,
+                 float pad_value, float scale, float* out_dev, const kapre_wave_desc* out_desc, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 const char* kapre_last_error(void);
 int kapre_version(void);

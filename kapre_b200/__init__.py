@@ -15,8 +15,10 @@ from .time_frequency import (  # noqa: E402
     Phase,
     MagnitudeToDecibel,
     ApplyFilterbank,
+    Delta,
     Layer,
 )
+from .signal import Frame, Energy, LogmelToMFCC  # noqa: E402
 from .composed import (  # noqa: E402
     Sequential,
     get_stft_magnitude_layer,
@@ -29,7 +31,7 @@ from .composed import (  # noqa: E402
 __all__ = [
     '__version__', 'VERSION', 'backend', 'composed',
     'STFT', 'InverseSTFT', 'Magnitude', 'Phase', 'MagnitudeToDecibel', 'ApplyFilterbank',
-    'Layer', 'Sequential',
+    'Delta', 'Frame', 'Energy', 'LogmelToMFCC', 'Layer', 'Sequential',
     'get_stft_magnitude_layer', 'get_melspectrogram_layer', 'get_log_frequency_spectrogram_layer',
     'get_perfectly_reconstructing_stft_istft', 'get_stft_mag_phase',
 ]

@@ -164,6 +164,75 @@ __global__ void kb_phase_kernel(const float2* __restrict__ x, float* __restrict_
     }
 }
 
+// ---- adjacent layers: Delta / Frame / Energy (element-wise or small-window kernels, HBM-bound) ----
+__device__ __forceinline__ long long kb_pad_index(long long t, long long T, int mode) {
+    // index into [0, T) for an out-of-range t under tf.pad's SYMMETRIC (0) / REFLECT (1); -1 = zero (CONSTANT)
+    if (t >= 0 && t < T) return t;
+    if (mode == 2) return -1;
+    if (t < 0) t = (mode == 0) ? (-t - 1) : (-t);
+    else t = (mode == 0) ? (2 * T - 1 - t) : (2 * T - 2 - t);
+    return (t >= 0 && t < T) ? t : -1;
+}
+
+__global__ void kb_delta_kernel(const float* __restrict__ x, float* __restrict__ y, long long outer, long long T,
+                                long long inner, int n, float inv_denom, int mode) {
+    const long long total = outer * T * inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long in = i % inner;
+        const long long t = (i / inner) % T;
+        const long long o = i / (inner * T);
+        const float* base = x + o * T * inner + in;
+        float acc = 0.0f;
+        for (int m = 1; m <= n; ++m) {
+            const long long tp = kb_pad_index(t + m, T, mode), tm = kb_pad_index(t - m, T, mode);
+            const float a = tp >= 0 ? base[tp * inner] : 0.0f;
+            const float b = tm >= 0 ? base[tm * inner] : 0.0f;
+            acc += (float)m * (a - b);
+        }
+        y[i] = acc * inv_denom;
+    }
+}
+
+__global__ void kb_frame_kernel(const float* __restrict__ x, long long x_sb, long long x_sc, long long x_sl, int B, int C,
+                                int L, int fl, int hop, int T, float pad_value, float* __restrict__ out, long long o_sb,
+                                long long o_sc, long long o_st, long long o_sk) {
+    const long long total = (long long)B * C * T * fl;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % fl);
+        const long long r = i / fl;
+        const int t = (int)(r % T);
+        const long long bc = r / T;
+        const int c = (int)(bc % C), b = (int)(bc / C);
+        const long long s = (long long)t * hop + n;
+        const float v = s < L ? x[b * x_sb + c * x_sc + s * x_sl] : pad_value;
+        out[b * o_sb + c * o_sc + t * o_st + n * o_sk] = v;
+    }
+}
+
+__global__ void kb_energy_kernel(const float* __restrict__ x, long long x_sb, long long x_sc, long long x_sl, int B, int C,
+                                 int L, int fl, int hop, int T, float pad_value, float scale, float* __restrict__ out,
+                                 long long o_sb, long long o_sc, long long o_st) {
+    const long long n_frames = (long long)B * C * T;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long f = warp0; f < n_frames; f += n_warps) {
+        const int t = (int)(f % T);
+        const long long bc = f / T;
+        const int c = (int)(bc % C), b = (int)(bc / C);
+        const float* xs = x + b * x_sb + c * x_sc;
+        float acc = 0.0f;
+        for (int n = lane; n < fl; n += 32) {
+            const long long s = (long long)t * hop + n;
+            const float v = s < L ? xs[s * x_sl] : pad_value;
+            acc += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[b * o_sb + c * o_sc + t * o_st] = scale * acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // plans
 // ------------------------------------------------------------------------------------------
@@ -767,6 +836,68 @@ int kapre_phase(const void* x_complex_dev, float* out_dev, int64_t n, void* stre
     int grid, rc;
     if ((rc = kb_ew_grid(n, &grid))) return rc;
     kb_phase_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)x_complex_dev, out_dev, n);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+static int kb_frames_for(int L, int fl, int hop, int pad_end) {
+    if (pad_end) return (L + hop - 1) / hop;
+    return L < fl ? 0 : 1 + (L - fl) / hop;
+}
+
+int kapre_delta(const float* x_dev, float* out_dev, int64_t outer, int64_t frames, int64_t inner, int win_length,
+                int pad_mode, void* stream) {
+    if (win_length < 3 || (win_length & 1) == 0) return kb_fail(KAPRE_E_INVALID, "win_length must be odd and >= 3, got %d", win_length);
+    if (pad_mode < 0 || pad_mode > 2) return kb_fail(KAPRE_E_INVALID, "bad pad_mode %d", pad_mode);
+    if (outer < 0 || frames < 0 || inner < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    const long long total = (long long)outer * frames * inner;
+    if (total == 0) return 0;
+    if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    if (x_dev == out_dev) return kb_fail(KAPRE_E_INVALID, "delta cannot run in place");
+    const int n = (win_length - 1) / 2;
+    double denom = 0;
+    for (int m = 1; m <= n; ++m) denom += 2.0 * m * m;
+    int grid, rc;
+    if ((rc = kb_ew_grid(total, &grid))) return rc;
+    kb_delta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, out_dev, outer, frames, inner, n, (float)(1.0 / denom), pad_mode);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+int kapre_frame(const float* x_dev, const kapre_wave_desc* xd, int frame_length, int hop_length, int pad_end, float pad_value,
+                float* out_dev, const kapre_spec_desc* od, void* stream) {
+    if (!xd || !od) return kb_fail(KAPRE_E_INVALID, "null argument");
+    if (frame_length <= 0 || hop_length <= 0) return kb_fail(KAPRE_E_INVALID, "frame_length and hop_length must be positive");
+    const int T = kb_frames_for(xd->length, frame_length, hop_length, pad_end);
+    const long long total = (long long)xd->batch * xd->channels * T * frame_length;
+    if (total <= 0) return 0;
+    if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    int grid, rc;
+    if ((rc = kb_ew_grid(total, &grid))) return rc;
+    kb_frame_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, xd->stride_b, xd->stride_c, xd->stride_l, xd->batch,
+                                                          xd->channels, xd->length, frame_length, hop_length, T, pad_value,
+                                                          out_dev, od->stride_b, od->stride_c, od->stride_t, od->stride_f);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+int kapre_energy(const float* x_dev, const kapre_wave_desc* xd, int frame_length, int hop_length, int pad_end, float pad_value,
+                 float scale, float* out_dev, const kapre_wave_desc* od, void* stream) {
+    if (!xd || !od) return kb_fail(KAPRE_E_INVALID, "null argument");
+    if (frame_length <= 0 || hop_length <= 0) return kb_fail(KAPRE_E_INVALID, "frame_length and hop_length must be positive");
+    const int T = kb_frames_for(xd->length, frame_length, hop_length, pad_end);
+    const long long n_frames = (long long)xd->batch * xd->channels * T;
+    if (n_frames <= 0) return 0;
+    if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    if (od->length != T) return kb_fail(KAPRE_E_INVALID, "output must have %d frames, got %d", T, od->length);
+    int grid, rc;
+    if ((rc = kb_ew_grid(n_frames * 32, &grid))) return rc;
+    kb_energy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, xd->stride_b, xd->stride_c, xd->stride_l, xd->batch,
+                                                           xd->channels, xd->length, frame_length, hop_length, T, pad_value,
+                                                           scale, out_dev, od->stride_b, od->stride_c, od->stride_l);
     KB_CUDA(cudaGetLastError());
     g_launches++;
     return 0;

@@ -308,3 +308,64 @@ def magnitude_to_decibel(x, ref_value=1.0, amin=1e-5, dynamic_range=80.0):
         N.check(N.lib().kapre_magnitude_to_decibel(_ptr(t), _ptr(out), n_items, item, ctypes.byref(dbc), _ptr(ws),
                                                    _stream_ptr()))
     return to_host(out) if was_host and isinstance(x, np.ndarray) else out
+
+
+# ------------------------------------------------------------------------------- adjacent layers
+_PAD_MODES = {'symmetric': 0, 'reflect': 1, 'constant': 2}
+
+
+def delta(x: torch.Tensor, win_length: int, mode: str, data_format: str):
+    """kapre.Delta along the time axis of (b, t, f, ch) / (b, ch, t, f)."""
+    if not x.is_cuda:
+        raise N.KapreNativeError('delta needs a CUDA tensor')
+    x = x.float().contiguous()
+    if x.dim() != 4:
+        raise ValueError('Delta expects a 4-D batch, got shape %s' % (tuple(x.shape),))
+    if data_format == _CH_LAST_STR:
+        outer, frames, inner = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    else:
+        outer, frames, inner = x.shape[0] * x.shape[1], x.shape[2], x.shape[3]
+    out = torch.empty_like(x)
+    if x.numel():
+        N.check(N.lib().kapre_delta(_ptr(x), _ptr(out), outer, frames, inner, int(win_length),
+                                    _PAD_MODES[mode.lower()], _stream_ptr()))
+    return out
+
+
+def _frames_for(length, frame_length, hop, pad_end):
+    return -(-length // hop) if pad_end else max(0, 1 + (length - frame_length) // hop)
+
+
+def frame(x: torch.Tensor, frame_length, hop_length, pad_end, pad_value, data_format):
+    """kapre.Frame: (b, t, ch) -> (b, frames, frame_length, ch) or (b, ch, t) -> (b, ch, frames, frame_length)."""
+    if not x.is_cuda:
+        raise N.KapreNativeError('frame needs a CUDA tensor')
+    x = x.float()
+    xd, (B, C, L) = _wave_desc(x, data_format)
+    T = _frames_for(L, frame_length, hop_length, pad_end)
+    out, od = _spec_alloc(B, C, T, frame_length, data_format, torch.float32, x.device)
+    if out.numel():
+        N.check(N.lib().kapre_frame(_ptr(x), ctypes.byref(xd), int(frame_length), int(hop_length), int(bool(pad_end)),
+                                    ctypes.c_float(pad_value), _ptr(out), ctypes.byref(od), _stream_ptr()))
+    return out
+
+
+def energy(x: torch.Tensor, frame_length, hop_length, pad_end, pad_value, scale, data_format):
+    """kapre.Energy: scale * sum of squares per frame; (b, t, ch) -> (b, frames, ch), (b, ch, t) -> (b, ch, frames)."""
+    if not x.is_cuda:
+        raise N.KapreNativeError('energy needs a CUDA tensor')
+    x = x.float()
+    xd, (B, C, L) = _wave_desc(x, data_format)
+    T = _frames_for(L, frame_length, hop_length, pad_end)
+    if data_format == _CH_LAST_STR:
+        out = torch.empty((B, T, C), dtype=torch.float32, device=x.device)
+        sb, st, sc = out.stride()
+    else:
+        out = torch.empty((B, C, T), dtype=torch.float32, device=x.device)
+        sb, sc, st = out.stride()
+    if out.numel():
+        od = N.WaveDesc(B, C, T, sb, sc, st)
+        N.check(N.lib().kapre_energy(_ptr(x), ctypes.byref(xd), int(frame_length), int(hop_length), int(bool(pad_end)),
+                                     ctypes.c_float(pad_value), ctypes.c_float(scale), _ptr(out), ctypes.byref(od),
+                                     _stream_ptr()))
+    return out

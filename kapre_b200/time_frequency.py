@@ -21,7 +21,7 @@ from . import _native as N
 from . import backend, ops
 from .backend import _CH_DEFAULT_STR, _CH_FIRST_STR, _CH_LAST_STR
 
-__all__ = ['Layer', 'STFT', 'InverseSTFT', 'Magnitude', 'Phase', 'MagnitudeToDecibel', 'ApplyFilterbank']
+__all__ = ['Layer', 'STFT', 'InverseSTFT', 'Magnitude', 'Phase', 'MagnitudeToDecibel', 'ApplyFilterbank', 'Delta']
 
 _name_counters = {}
 _REGISTRY = {}
@@ -302,4 +302,37 @@ class ApplyFilterbank(Layer):
         config = super().get_config()
         config.update({'type': self.type, 'filterbank_kwargs': self.filterbank_kwargs,
                        'data_format': self.data_format_original})
+        return config
+
+
+@register_keras_serializable(package='Kapre')
+class Delta(Layer):
+    """Local estimate of the time derivative (reference: kapre/time_frequency.py:563-644):
+    ``sum_{m=-n..n} m * x[t+m] / (2 * sum_{m=1..n} m^2)`` with ``n = (win_length - 1) // 2`` on the time
+    axis, the input extended by ``mode`` ('symmetric', 'reflect' or 'constant', as ``tf.pad``)."""
+
+    def __init__(self, win_length=5, mode='symmetric', data_format='default', **kwargs):
+        super().__init__(**kwargs)
+        backend.validate_data_format_str(data_format)
+        data_format = _unwrap_format(data_format)
+        if not win_length >= 3:
+            raise ValueError('win_length should be equal or bigger than 3, but it is %d' % win_length)
+        if win_length % 2 != 1:
+            raise ValueError('win_length should be an odd number, but it is %d' % win_length)
+        if mode.lower() not in ('symmetric', 'reflect', 'constant'):
+            raise ValueError('mode.lower() should be one of %sbut it is %s'
+                             % (str(('symmetric', 'reflect', 'constant')), mode))
+        self.data_format_original = data_format
+        self.data_format = _resolve(data_format)
+        self.win_length = win_length
+        self.mode = mode
+        self.n = (self.win_length - 1) // 2
+        self.denom = 2 * sum([_n ** 2 for _n in range(1, self.n + 1, 1)])
+
+    def call(self, x):
+        return ops.delta(x, self.win_length, self.mode, self.data_format)
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({'win_length': self.win_length, 'mode': self.mode, 'data_format': self.data_format_original})
         return config

@@ -20,6 +20,7 @@ __all__ = [
     'hz_to_mel', 'mel_to_hz', 'filterbank_mel', 'filterbank_log', 'apply_filterbank',
     'magnitude_to_decibel', 'inverse_stft_window', 'inverse_stft_frames', 'istft_layer',
     'melspectrogram_layer', 'stft_magnitude_layer', 'phase', 'stft_mag_phase_layer',
+    'delta', 'frame_layer', 'energy_layer', 'logmel_to_mfcc',
 ]
 
 CH_FIRST = 'channels_first'
@@ -363,3 +364,67 @@ def stft_mag_phase_layer(x, n_fft=2048, win_length=None, hop_length=None, window
         mag = magnitude_to_decibel(mag, db_ref_value, db_amin, db_dynamic_range)
     ch_axis = 1 if output_data_format == CH_FIRST else 3
     return np.concatenate([mag, ph.astype(mag.dtype)], axis=ch_axis)
+
+
+def delta(x, win_length=5, mode='symmetric', data_format='default'):
+    """kapre.Delta.call, kapre/time_frequency.py:613-636: tf.pad(mode) over time, correlate with
+    arange(-n, n+1), divide by 2*sum(m^2)."""
+    df = resolve_data_format(data_format)
+    x = np.asarray(x, dtype=np.float64)
+    if df == CH_FIRST:
+        x = np.transpose(x, (0, 2, 3, 1))
+    n = (win_length - 1) // 2
+    denom = 2 * sum(m * m for m in range(1, n + 1))
+    xp = np.pad(x, [(0, 0), (n, n), (0, 0), (0, 0)], mode=mode.lower())
+    T = x.shape[1]
+    out = np.zeros_like(x)
+    for j, m in enumerate(range(-n, n + 1)):
+        out += m * xp[:, j:j + T]
+    out /= denom
+    if df == CH_FIRST:
+        out = np.transpose(out, (0, 3, 1, 2))
+    return out
+
+
+def frame_layer(x, frame_length, hop_length, pad_end=False, pad_value=0, data_format='default'):
+    """kapre.Frame.call, kapre/signal.py:88-104 (tf.signal.frame along the time axis)."""
+    df = resolve_data_format(data_format)
+    x = np.asarray(x, dtype=np.float64)
+    if df == CH_LAST:
+        x = np.transpose(x, (0, 2, 1))
+    L = x.shape[-1]
+    T = num_frames(L, frame_length, hop_length, pad_end)
+    need = (T - 1) * hop_length + frame_length if T > 0 else 0
+    if need > L:
+        x = np.pad(x, [(0, 0), (0, 0), (0, need - L)], constant_values=pad_value)
+    idx = np.arange(T)[:, None] * hop_length + np.arange(frame_length)[None, :]
+    fr = x[..., idx]                       # (b, ch, T, frame_length)
+    if df == CH_LAST:
+        fr = np.transpose(fr, (0, 2, 3, 1))  # (b, T, frame_length, ch)
+    return fr
+
+
+def energy_layer(x, sample_rate=22050, ref_duration=0.1, frame_length=2205, hop_length=1102, pad_end=False,
+                 pad_value=0, data_format='default'):
+    """kapre.Energy.call, kapre/signal.py:181-212."""
+    df = resolve_data_format(data_format)
+    fr = frame_layer(x, frame_length, hop_length, pad_end, pad_value, data_format)
+    e = np.sum(fr ** 2, axis=2 if df == CH_LAST else 3)
+    return ref_duration / (frame_length / sample_rate) * e
+
+
+def logmel_to_mfcc(x, n_mfccs=20, data_format='default'):
+    """kapre.LogmelToMFCC.call, kapre/signal.py:418-437 -> tf.signal.mfccs_from_log_mel_spectrograms:
+    dct(type=2)(x) * rsqrt(2 * n_mels), i.e. sqrt(2/N) * sum_n x[n] cos(pi k (2n+1) / (2N)); first n_mfccs."""
+    df = resolve_data_format(data_format)
+    x = np.asarray(x, dtype=np.float64)
+    if df == CH_LAST:
+        x = np.transpose(x, (0, 1, 3, 2))
+    N = x.shape[-1]
+    n = np.arange(N)[:, None]
+    k = np.arange(N)[None, :]
+    mat = 2.0 * np.cos(np.pi * k * (2 * n + 1) / (2.0 * N)) / np.sqrt(2.0 * N)
+    y = (x @ mat)[..., :n_mfccs]
+    if df == CH_LAST:
+        y = np.transpose(y, (0, 1, 3, 2))
+    return y

@@ -443,3 +443,57 @@ def test_stft_mag_phase(K, golden, fmt, n_fft, hop, db):
     refm = np.abs(golden['stft_512_256_hann_window'])
     refm = refm[None] if fmt == 'channels_first' else refm[:, :, None]
     np.testing.assert_allclose(mag, refm, atol=2e-4)
+
+
+# ------------------------------------------------------------------------------- "next" rows: Delta, Frame, Energy, MFCC
+def test_delta_literal_and_modes(K):
+    """tests/test_time_frequency.py:375-387 (literal KAT) + all modes / formats vs the oracle."""
+    x = np.array([1.0, 2.0, 3.0, 4.0], dtype=np.float32).reshape(1, -1, 1, 1)
+    got = K.Delta(win_length=3, data_format='channels_last')(x)
+    np.testing.assert_allclose(got, np.array([0.5, 1.0, 1.0, 0.5], np.float32).reshape(1, -1, 1, 1))
+    rng = np.random.default_rng(0)
+    for fmt in ('channels_first', 'channels_last'):
+        shape = (2, 3, 17, 40) if fmt == 'channels_first' else (2, 17, 40, 3)
+        x = rng.normal(size=shape).astype(np.float32)
+        for mode in ('symmetric', 'reflect', 'constant'):
+            for win in (3, 5, 9):
+                got = K.Delta(win_length=win, mode=mode, data_format=fmt)(x)
+                ref = O.delta(x, win, mode, fmt)
+                np.testing.assert_allclose(got, ref, atol=2e-6)
+    with pytest.raises(ValueError):
+        K.Delta(win_length=4)
+    with pytest.raises(ValueError):
+        K.Delta(mode='wrap')
+
+
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('pad_end', [False, True])
+def test_frame_and_energy(K, fmt, pad_end):
+    """Mirrors of tests/test_signal.py (Frame / Energy) against the oracle."""
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, size=(2, 3, 5000) if fmt == 'channels_first' else (2, 5000, 3)).astype(np.float32)
+    got = K.Frame(frame_length=1024, hop_length=300, pad_end=pad_end, pad_value=0.25, data_format=fmt)(x)
+    ref = O.frame_layer(x, 1024, 300, pad_end, 0.25, fmt)
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got, ref.astype(np.float32))
+    e = K.Energy(sample_rate=16000, ref_duration=0.05, frame_length=800, hop_length=400, pad_end=pad_end,
+                 data_format=fmt)(x)
+    eref = O.energy_layer(x, 16000, 0.05, 800, 400, pad_end, 0, fmt)
+    assert e.shape == eref.shape
+    np.testing.assert_allclose(e, eref, rtol=2e-6)
+    with pytest.raises(ValueError):
+        K.Frame(frame_length=100, hop_length=200)
+
+
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_logmel_to_mfcc(K, fmt):
+    """Mirror of tests/test_signal.py:79-106: HTK-scaled DCT-II of the log-mel spectrogram."""
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-1, 1, size=(3, 9000, 2)).astype(np.float32)
+    kw = dict(n_fft=512, hop_length=128, sample_rate=16000, n_mels=40, return_decibel=True)
+    mel = K.get_melspectrogram_layer(output_data_format=fmt, **kw)
+    seq = K.Sequential(list(mel.layers) + [K.LogmelToMFCC(n_mfccs=13, data_format=fmt)])
+    got = seq(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.logmel_to_mfcc(O.melspectrogram_layer(x, output_data_format=fmt, **kw), 13, fmt)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 5e-4

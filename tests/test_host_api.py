@@ -154,3 +154,53 @@ def test_abi_exports_every_declared_symbol():
     w = np.ones(8, np.float32)
     rc = lib.kapre_stft_plan_create(0, 8, 2, w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(out))
     assert rc == -1 and b'out of range' in lib.kapre_last_error()
+
+
+def test_adjacent_layers_config_and_validation():
+    """Delta / Frame / Energy / LogmelToMFCC mirror the reference's arguments and errors
+    (kapre/time_frequency.py:563-644, kapre/signal.py:22-233, :365-447)."""
+    import kapre_b200 as K
+    d = K.Delta(win_length=7, mode='reflect', data_format='channels_first')
+    cfg = d.get_config()
+    assert (cfg['win_length'], cfg['mode'], cfg['data_format']) == (7, 'reflect', 'channels_first')
+    assert d.n == 3 and d.denom == 2 * (1 + 4 + 9)
+    for bad in (dict(win_length=2), dict(win_length=4), dict(mode='wrap'), dict(data_format='weird')):
+        with pytest.raises(ValueError):
+            K.Delta(**bad)
+    f = K.Frame(frame_length=512, hop_length=128, pad_end=True, pad_value=1, data_format='channels_last')
+    assert K.Frame.from_config(f.get_config()).get_config() == f.get_config()
+    e = K.Energy(sample_rate=8000, frame_length=400, hop_length=200)
+    assert e.get_config()['ref_duration'] == 0.1
+    m = K.LogmelToMFCC(n_mfccs=13)
+    assert m.get_config()['n_mfccs'] == 13
+    import kapre
+    assert kapre.signal.Frame is K.Frame and kapre.Delta is K.Delta
+
+
+def test_dct_matrix_matches_oracle_and_scipy():
+    import scipy.fft
+    from kapre_b200.signal import dct2_htk_matrix
+    from oracle import reference as O
+    x = np.random.default_rng(0).normal(size=(2, 5, 40, 1))
+    ref = O.logmel_to_mfcc(x, 13, 'channels_last')
+    mat = dct2_htk_matrix(40, 13).astype(np.float64)
+    got = np.einsum('btmc,mk->btkc', x, mat)
+    np.testing.assert_allclose(got, ref, atol=1e-5)
+    sp = scipy.fft.dct(x, type=2, axis=2)[:, :, :13] / np.sqrt(2 * 40)
+    np.testing.assert_allclose(ref, sp, atol=1e-10)
+
+
+def test_oracle_delta_frame_energy_known_answers():
+    from oracle import reference as O
+    x = np.array([1.0, 2.0, 3.0, 4.0]).reshape(1, -1, 1, 1)
+    np.testing.assert_allclose(O.delta(x, 3, 'symmetric', 'channels_last').ravel(), [0.5, 1.0, 1.0, 0.5])
+    w = np.arange(10, dtype=np.float64).reshape(1, 10, 1)
+    fr = O.frame_layer(w, 4, 3, False, 0, 'channels_last')
+    assert fr.shape == (1, 3, 4, 1)
+    np.testing.assert_array_equal(fr[0, :, :, 0], [[0, 1, 2, 3], [3, 4, 5, 6], [6, 7, 8, 9]])
+    fr = O.frame_layer(w, 4, 3, True, -1, 'channels_last')
+    assert fr.shape == (1, 4, 4, 1)
+    np.testing.assert_array_equal(fr[0, 3, :, 0], [9, -1, -1, -1])
+    en = O.energy_layer(np.ones((1, 8, 1)), sample_rate=4, ref_duration=1.0, frame_length=4, hop_length=4,
+                        data_format='channels_last')
+    np.testing.assert_allclose(en.ravel(), [4.0, 4.0])
