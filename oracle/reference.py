@@ -48,17 +48,53 @@ def get_window(window_name, length: int, dtype=np.float64) -> np.ndarray:
     """
     if window_name is None:
         window_name = 'hann_window'
+    W = int(length)
+    if window_name in ('kaiser_window', 'kaiser_bessel_derived_window', 'vorbis_window'):
+        return _other_window(window_name, W).astype(dtype)     # backend.py:82-87
     coeffs = {'hann_window': (0.5, 0.5), 'hamming_window': (0.54, 0.46)}
     if window_name not in coeffs:
         raise NotImplementedError('Window name %s is not supported' % window_name)  # backend.py:89-98
     a, b = coeffs[window_name]
-    W = int(length)
     if W == 1:
         return np.ones(1, dtype=dtype)
     even = 1 - W % 2
     D = W + even - 1
     n = np.arange(W, dtype=np.float64)
     return (a - b * np.cos(2.0 * np.pi * n / D)).astype(dtype)
+
+
+def _bessel_i0(x):
+    """Modified Bessel function I0 by its power series sum_k ((x/2)^k / k!)^2 (converges fast for x <= ~30)."""
+    x = np.asarray(x, dtype=np.float64)
+    term = np.ones_like(x)
+    total = np.ones_like(x)
+    for k in range(1, 200):
+        term = term * (x / (2.0 * k)) ** 2
+        total = total + term
+    return total
+
+
+def _other_window(name, W):
+    """tf.signal.kaiser_window / kaiser_bessel_derived_window / vorbis_window with TF's default beta=12
+    (kapre passes only the length, time_frequency.py:178).  Kaiser: I0(beta*sqrt(1-r^2))/I0(beta),
+    r = 2n/(W-1)-1; KBD: sqrt of the normalised running sum of a (W/2+1)-point Kaiser, mirrored;
+    Vorbis: sin(pi/2 * sin^2(pi*(n+1/2)/W))."""
+    beta = 12.0
+
+    def kaiser(m):
+        if m == 1:
+            return np.ones(1)
+        r = 2.0 * np.arange(m, dtype=np.float64) / (m - 1) - 1.0
+        return _bessel_i0(beta * np.sqrt(np.maximum(0.0, 1.0 - r * r))) / _bessel_i0(beta)
+
+    if name == 'kaiser_window':
+        return kaiser(W)
+    if name == 'kaiser_bessel_derived_window':
+        cs = np.cumsum(kaiser(W // 2 + 1))
+        half = np.sqrt(cs[:-1] / cs[-1])
+        return np.concatenate([half, half[::-1]])
+    n = np.arange(W, dtype=np.float64) + 0.5
+    return np.sin(np.pi / 2.0 * np.sin(np.pi * n / W) ** 2)
 
 
 # --------------------------------------------------------------------------- framing / STFT

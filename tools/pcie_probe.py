@@ -1,0 +1,68 @@
+"""Measures the PCIe ceiling of the end-to-end number: pinned H2D / D2H copies of the cfg2 step's
+buffers alone and together, then predict() with different chunk counts."""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, '.')
+import kapre_b200 as K
+
+
+def timeit(fn, n=10):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n
+
+
+def main():
+    B, L = 256, 110250
+    layer = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128,
+                                       return_decibel=True, input_data_format='channels_last',
+                                       output_data_format='channels_last')
+    xh = torch.empty((B, L, 1), dtype=torch.float32, pin_memory=True)
+    xh.uniform_(-1, 1)
+    xd = torch.empty_like(xh, device='cuda')
+    yd = layer(xd)
+    yh = torch.empty(yd.shape, dtype=yd.dtype, pin_memory=True)
+    frames = B * yd.shape[1]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    res = {'in_bytes': xh.numel() * 4, 'out_bytes': yh.numel() * 4, 'frames': frames}
+
+    def h2d():
+        xd.copy_(xh, non_blocking=True)
+
+    def d2h():
+        yh.copy_(yd, non_blocking=True)
+
+    def both():
+        with torch.cuda.stream(s1):
+            xd.copy_(xh, non_blocking=True)
+        with torch.cuda.stream(s2):
+            yh.copy_(yd, non_blocking=True)
+
+    t = timeit(h2d)
+    res['h2d_ms'] = t * 1e3
+    res['h2d_GBs'] = res['in_bytes'] / t / 1e9
+    t = timeit(d2h)
+    res['d2h_ms'] = t * 1e3
+    res['d2h_GBs'] = res['out_bytes'] / t / 1e9
+    t = timeit(both)
+    res['both_ms'] = t * 1e3
+    res['pcie_bound_frames_per_s'] = frames / t
+    for chunks in (1, 2, 4, 8, 16, 32, 64):
+        bs = -(-B // chunks)
+        t = timeit(lambda: layer.predict(xh, batch_size=bs), n=8)
+        res['predict_chunks_%d_ms' % chunks] = t * 1e3
+        res['predict_chunks_%d_fps' % chunks] = frames / t
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == '__main__':
+    main()
