@@ -260,6 +260,9 @@ struct kapre_stft_plan {
     int n_fft, win_length, hop, Q;
     DevInfo dev;
     float* wh = nullptr;      // fused path: 0.5 * window padded to n_fft
+    kb_f4* cwq = nullptr;     // cosine-sum window factors (cosw), see KbStftParams
+    int cosw = 0;
+    float cw_a0 = 0.0f;
     float2* twp = nullptr;
     float2* twn = nullptr;
     float* w = nullptr;       // generic path: window[0, win_eff)
@@ -486,6 +489,14 @@ int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const floa
         if ((rc = kb_upload(wh, &p->wh)) || (rc = kb_upload(twp, &p->twp)) || (rc = kb_upload(twn, &p->twn))) {
             kapre_stft_plan_destroy(p); return rc;
         }
+        double ca = 0.0, cb = 0.0;
+        if (kb_fit_cosine_window(window_host, win_length, n_fft, &ca, &cb) && kb_env_int("KAPRE_B200_NOCOSW", 0) == 0) {
+            std::vector<kb_f4> cwq;
+            kb_make_cwq(p->Q, n_fft, cb, cwq);
+            if ((rc = kb_upload(cwq, &p->cwq))) { kapre_stft_plan_destroy(p); return rc; }
+            p->cosw = 1;
+            p->cw_a0 = (float)(0.5 * ca);
+        }
     }
     {   // generic tables are always built: they also serve sizes the fused kernel cannot take
         std::vector<float> w(window_host, window_host + p->win_eff);
@@ -502,7 +513,7 @@ int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const floa
 
 void kapre_stft_plan_destroy(kapre_stft_plan* p) {
     if (!p) return;
-    cudaFree(p->wh); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->w); cudaFree(p->tw);
+    cudaFree(p->wh); cudaFree(p->cwq); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->w); cudaFree(p->tw);
     delete p;
 }
 
@@ -589,6 +600,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     p.x_lo = x_dev; p.x_hi = x_dev + max_off + 1; p.x_numel = max_off + 1;
     p.x_align = (unsigned)(((uintptr_t)x_dev >> 2) & 3); p.bulk_ok = bulk ? 1 : 0; p.dbuf = 0;
     p.wh = plan->wh; p.twp = plan->twp; p.twn = plan->twn;
+    p.cosw = plan->cosw; p.cw_a0 = plan->cw_a0; p.cwq = plan->cwq;
     p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
     p.mode = mode;
     if (fbmode) {
@@ -600,6 +612,12 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
     const long long tiles = (long long)B * C * p.n_tiles_t;
     if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
+    const int force_bps = kb_env_int("KAPRE_B200_BPS", 0);   // experiment: CTAs per SM (occupancy study)
+    if (force_bps > 0 && force_bps < cfg.bps) {
+        cfg.bps = force_bps;
+        const int want = (228 * 1024) / force_bps - 2048;   // pad the request so that no more CTAs fit
+        if (want > cfg.smem && want <= plan->dev.smem_optin) cfg.smem = want;
+    }
     long long gmax = (long long)plan->dev.sm_count * cfg.bps;
     const int grid = (int)(tiles < gmax ? tiles : gmax);
     switch (plan->Q) {

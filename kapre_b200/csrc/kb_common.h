@@ -60,6 +60,12 @@ struct KbStftParams {
     const float* wh;
     const float2* twp;
     const float2* twn;
+    // cosine-sum windows (hann, hamming, ... with win_length == n_fft): 0.5*w[n] = cw_a0 - B cos(2 pi n / n_fft)
+    // is evaluated in registers instead of loaded: cwq[q] = B * (cos a_e, cos a_o, sin a_e, sin a_o) with
+    // a_e = 2 pi (2q) / n_fft, a_o = 2 pi (2q + 1) / n_fft; the other factor exp(2 pi i j / 32) is a constant.
+    int cosw;
+    float cw_a0;
+    const kb_f4* cwq;
     // output, element strides (batch, channel, frame, bin)
     void* out;
     long long o_sb, o_sc, o_st, o_sk;
@@ -173,6 +179,14 @@ KB_HD cpx cscale(cpx a, float s) {
     return kb_up(kb_mul2(kb_pk(a.re, a.im), kb_pk(s, s)));
 #else
     return cmake(a.re * s, a.im * s);
+#endif
+}
+// a * s + c element-wise for a real scalar s (one packed FMA)
+KB_HD cpx cfma_s(cpx a, float s, cpx c) {
+#if defined(__CUDA_ARCH__)
+    return kb_up(kb_fma2(kb_pk(a.re, a.im), kb_pk(s, s), kb_pk(c.re, c.im)));
+#else
+    return cmake(a.re * s + c.re, a.im * s + c.im);
 #endif
 }
 // d * (c - i sn): twiddle with separately given cosine / sine (compile-time constants at the call sites)

@@ -48,6 +48,34 @@ static inline void kb_make_wh(const float* window, int win_length, int n_fft, st
     for (int i = 0; i < n; ++i) out[i] = 0.5f * window[i];
 }
 
+// Is the analysis window a cosine-sum window a - b cos(2 pi n / n_fft) over exactly n_fft samples?
+// (tf.signal.hann_window / hamming_window with win_length == n_fft, n_fft even.)  tol: the table
+// passed in is float32, so 3e-7 covers its rounding.
+static inline bool kb_fit_cosine_window(const float* window, int win_length, int n_fft, double* a, double* b) {
+    if (win_length != n_fft || (n_fft & 1)) return false;
+    const double w0 = window[0], wm = window[n_fft / 2];
+    *a = 0.5 * (w0 + wm);
+    *b = 0.5 * (wm - w0);
+    for (int n = 0; n < n_fft; ++n) {
+        const double fit = *a - *b * cos(2.0 * M_PI * (double)n / (double)n_fft);
+        if (fabs(fit - (double)window[n]) > 3e-7) return false;
+    }
+    return true;
+}
+
+// Per-lane factors of the in-register window (KbStftParams::cwq), pre-scaled by 0.5 * b.
+static inline void kb_make_cwq(int Q, int n_fft, double b, std::vector<kb_f4>& out) {
+    out.resize(Q);
+    for (int q = 0; q < Q; ++q) {
+        const double ae = 2.0 * M_PI * (double)(2 * q) / (double)n_fft;
+        const double ao = 2.0 * M_PI * (double)(2 * q + 1) / (double)n_fft;
+        kb_f4 v;
+        v.x = (float)(0.5 * b * cos(ae)); v.y = (float)(0.5 * b * cos(ao));
+        v.z = (float)(0.5 * b * sin(ae)); v.w = (float)(0.5 * b * sin(ao));
+        out[q] = v;
+    }
+}
+
 // Banded form of a (n_freq x n_bands) row-major filterbank: per band the tight support
 // [lo, hi) of its non-zero weights (interior zeros kept), zero-padded so that both the offset
 // into the weight array and hi - lo are multiples of 4 (hi may exceed n_freq by up to 3: the

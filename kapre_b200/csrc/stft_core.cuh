@@ -28,7 +28,7 @@
 #include "fft_regs.cuh"
 
 struct KbStftSmem {
-    int wh, twp, twn, cw, cm, cg, bar, plan, samples, outs, ex, total;  // byte offsets
+    int wh, twp, twn, cwq, cw, cm, cg, bar, plan, samples, outs, ex, total;  // byte offsets
     int span;       // samples staged per tile
     int exw;        // complex elements per warp in the exchange buffer (incl. bank skew)
     int Mp;         // padded band stride of out_s
@@ -52,6 +52,7 @@ KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_wa
     s.wh = off;  off += kb_align16(n_fft * 4);
     s.twp = off; off += kb_align16(Q * 33 * 8);
     s.twn = off; off += kb_align16((P / 2) * 8);
+    s.cwq = off; off += Q * 16;
     s.cw = off; if (fb) off += n_chunks * 16;
     s.cm = off; if (fb) off += kb_align16(n_chunks * 8);
     s.cg = off; if (fb) off += kb_align16(33 * 4);
@@ -286,7 +287,6 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     constexpr int P = 32 * Q;        // complex FFT length
     constexpr int FPW = 32 / Q;      // frames per warp per round
     constexpr int ZSTR = P + Q;      // frame stride (complex) of the natural-order buffer
-    constexpr int EXW = 32 * 33;     // complex elements per warp in the exchange buffer
     constexpr bool fbmode = (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB);
     constexpr bool dbmode = (MODE == KB_OUT_MAG_DB || MODE == KB_OUT_FB_DB);
     const bool dbany = dbmode || (MODE == KB_OUT_MAG_PHASE && p.db_on);   // per-item maximum needed
@@ -298,6 +298,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
     cpx* __restrict__ twp_s = reinterpret_cast<cpx*>(smem + L.twp);
     cpx* __restrict__ twn_s = reinterpret_cast<cpx*>(smem + L.twn);
+    kb_f4* __restrict__ cwq_s = reinterpret_cast<kb_f4*>(smem + L.cwq);
     kb_f4* __restrict__ cw_s = reinterpret_cast<kb_f4*>(smem + L.cw);
     kb_i2* __restrict__ cm_s = reinterpret_cast<kb_i2*>(smem + L.cm);
     int* __restrict__ cg_s = reinterpret_cast<int*>(smem + L.cg);
@@ -325,6 +326,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         for (int i = tid; i < N; i += kb_nt) wh_s[i] = p.wh[i];
         for (int i = tid; i < Q * 33; i += kb_nt) { float2 t = p.twp[i]; twp_s[i] = cmake(t.x, t.y); }
         for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
+        if (p.cosw) { for (int i = tid; i < Q; i += kb_nt) cwq_s[i] = p.cwq[i]; }
         if (fbmode) {
             for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
             for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.cg[i];
@@ -375,7 +377,23 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int col = round * FR + warp * FPW + g;
                 if (col < TF) {
                     const float* fr = smp_s + col * H;
-                    if (even_base) {
+                    if (even_base && p.cosw) {
+                        // window in registers: 0.5 w[2(q + Q j) + {0,1}] = a0 - cc * cos(2 pi j / 32) + ss * sin(2 pi j / 32)
+                        const kb_f4 cq = cwq_s[q];
+                        const cpx cc = cmake(cq.x, cq.y), ss = cmake(cq.z, cq.w);
+                        const cpx a0 = cmake(p.cw_a0, p.cw_a0);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n2 = 2 * (q + Q * j);
+                            const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
+                            const float cj = j <= 16 ? kb_cos32(j) : kb_cos32(32 - j);
+                            const float sj = j <= 16 ? kb_sin32(j) : -kb_sin32(32 - j);
+                            cpx wv = a0;
+                            if (cj != 0.0f) wv = cfma_s(cc, -cj, wv);
+                            if (sj != 0.0f) wv = cfma_s(ss, sj, wv);
+                            R.v[j] = cmul_elem(xv, wv);
+                        }
+                    } else if (even_base) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n2 = 2 * (q + Q * j);

@@ -3,6 +3,7 @@
 // loop over the CTA's threads; lets `pytest -m "not gpu"` validate the index arithmetic of
 // the fused kernels against the oracle in a container that has no GPU.
 #define KB_HOST_EMU 1
+#include <cstdlib>
 #include <cstdio>
 #include <vector>
 #include "../../kapre_b200/csrc/kb_tables.h"
@@ -67,6 +68,14 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
     p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left;
     p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data();
+    std::vector<kb_f4> cwq;
+    {
+        double ca = 0.0, cb = 0.0;
+        if (kb_fit_cosine_window(window, win_length, n_fft, &ca, &cb) && !getenv("KAPRE_B200_NOCOSW")) {
+            kb_make_cwq(Q, n_fft, cb, cwq);
+            p.cosw = 1; p.cw_a0 = (float)(0.5 * ca); p.cwq = cwq.data();
+        }
+    }
     p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
     p.bands = fb ? bands.data() : nullptr; p.fbw = fb ? fbw.data() : nullptr; p.n_bands = fb ? n_bands : 0;
     p.n_fbw = fb ? (int)fbw.size() : 0;

@@ -174,5 +174,17 @@ def test_cuda_reproduces_reference_run(key):
         assert d[ok].max() < 2e-3
         return
     tol = _gpu_tolerance(case, want)
-    err = float(np.abs(got.astype(want.dtype) - want).max())
+    diff = np.abs(got.astype(want.dtype) - want)
+    kind, kw = case['kind'], case['kwargs']
+    if kind in ('MagnitudeToDecibel', 'backend.magnitude_to_decibel') or kw.get('return_decibel'):
+        # decibel outputs: values whose LINEAR magnitude sits at the fp32 round-off floor of the FFT
+        # (5e-7 of the item's peak, e.g. the far skirts of a pure tone around amin) are compared on
+        # the linear scale; everything else must agree to `tol` dB
+        lin_g, lin_w = 10.0 ** (got.astype(np.float64) / 10.0), 10.0 ** (want.astype(np.float64) / 10.0)
+        floor = 5e-7 * lin_w.reshape(lin_w.shape[0], -1).max(axis=1).reshape((-1,) + (1,) * (lin_w.ndim - 1)) \
+            if lin_w.ndim > 1 else 5e-7 * lin_w.max()
+        bad = (diff > tol) & (np.abs(lin_g - lin_w) > floor)
+        assert not bad.any(), (key, float(diff[bad].max()), tol)
+        return
+    err = float(diff.max())
     assert err <= tol, (key, err, tol)
