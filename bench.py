@@ -218,6 +218,33 @@ def main():
             return float(t.item())
         return v
 
+    # ---------------- end to end through predict() with pinned host buffers ---------------------
+    def run_e2e():
+        xh = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        for i, t in enumerate(xh):
+            t.copy_(xs[i])
+        torch.cuda.synchronize()
+        n = max(3, min(args.steps, 20))
+        y = None
+        for i in range(max(3, args.warmup)):     # same pattern as the timed loop (the previous result is still
+            y = layer.predict(xh[i % 2])         # alive when the next call starts), so the result pool is warm
+        barrier()
+        per_step = []
+        t0 = time.perf_counter()
+        for i in range(n):
+            t1 = time.perf_counter()
+            y = layer.predict(xh[i % 2])
+            per_step.append(round((time.perf_counter() - t1) * 1e3, 3))
+        torch.cuda.synchronize()
+        secs = reduce_max(time.perf_counter() - t0)
+        if os.environ.get('KAPRE_BENCH_DEBUG'):
+            print('[e2e per-step ms]', per_step, file=sys.stderr)
+        return xh, y, n, secs
+
+    e2e_first = bool(os.environ.get('KAPRE_BENCH_E2E_FIRST'))
+    if e2e_first:
+        xh, y_host, e2e_steps, e2e_s = run_e2e()
+
     # ---------------- device-resident throughput ------------------------------------------------
     outs = [None] * N_SETS
     for i in range(warmup):
@@ -244,20 +271,8 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * frames * args.steps / (ms_total * 1e-3)
 
-    # ---------------- end to end through predict() with pinned host buffers ---------------------
-    xh = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    for i, t in enumerate(xh):
-        t.copy_(xs[i])
-    torch.cuda.synchronize()
-    e2e_steps = max(3, min(args.steps, 20))
-    for i in range(max(3, args.warmup)):     # also lets the pinned-host allocator reach its steady state
-        layer.predict(xh[i % 2])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        y_host = layer.predict(xh[i % 2])
-    torch.cuda.synchronize()
-    e2e_s = reduce_max(time.perf_counter() - t0)
+    if not e2e_first:
+        xh, y_host, e2e_steps, e2e_s = run_e2e()
     e2e_value = world * frames * e2e_steps / e2e_s
     h2d = xh[0].numel() * 4
     d2h = int(y_host.size) * 4

@@ -9,6 +9,8 @@ launch (magnitudes never reach HBM); ``.layers`` remains usable one by one
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -90,6 +92,32 @@ class Sequential(Layer):
             x = layer.call(x)
         return x
 
+    def _pinned_result(self, shape, dtype):
+        """Page-locked result buffer and the NumPy array over it that ``predict`` returns.
+
+        ``cudaHostAlloc`` of a result-sized block costs 10-70 ms (measured: it was the whole gap between
+        predict() and the PCIe bound), so finished buffers are recycled.  A buffer is handed out again
+        only when the array returned for it -- and every view derived from it -- is gone: NumPy keeps the
+        array's ``base`` (a tensor aliasing the buffer) alive exactly that long, and a weak reference to
+        that base tells."""
+        pool = self.__dict__.setdefault('_result_pool', [])
+        entry = None
+        for e in pool:
+            if e['t'].shape == shape and e['t'].dtype == dtype and (e['ref'] is None or e['ref']() is None):
+                entry = e
+                break
+        if entry is None:
+            entry = {'t': torch.empty(shape, dtype=dtype, pin_memory=True), 'ref': None}
+            pool.append(entry)
+            if len(pool) > 4:       # drop one idle buffer of another shape / an older one
+                for i, e in enumerate(pool):
+                    if e is not entry and (e['ref'] is None or e['ref']() is None):
+                        del pool[i]
+                        break
+        arr = entry['t'].numpy()
+        entry['ref'] = weakref.ref(arr.base)
+        return entry['t'], arr
+
     def predict(self, x, batch_size=None, verbose=0, **kwargs):
         """Like ``keras.Model.predict``: host array in, host array out.
 
@@ -123,14 +151,14 @@ class Sequential(Layer):
             ev_c = torch.cuda.Event()
             ev_c.record(s_comp)
             if out_host is None:
-                out_host = torch.empty((B,) + tuple(yd.shape[1:]), dtype=yd.dtype, pin_memory=True)
+                out_host, out_arr = self._pinned_result((B,) + tuple(yd.shape[1:]), yd.dtype)
             s_out.wait_event(ev_c)
             yd.record_stream(s_out)
             with torch.cuda.stream(s_out):
                 out_host[i:i + chunk].copy_(yd, non_blocking=True)
             keep.append((xd, yd))
         s_out.synchronize()
-        return out_host.numpy()
+        return out_arr
 
     # -- serialisation ------------------------------------------------------------------------
     def get_config(self):

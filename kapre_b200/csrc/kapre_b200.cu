@@ -16,6 +16,7 @@
 #include "../../include/kapre_b200.h"
 #include "kb_tables.h"
 #include "stft_core.cuh"
+#include "stft_mc_core.cuh"
 #include "istft_core.cuh"
 #include "aux_core.cuh"
 
@@ -72,6 +73,13 @@ template <int Q, int MODE>
 __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel(const __grid_constant__ KbStftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
     kb_stft_cta<Q, MODE>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// multi-channel tiles (interleaved tensors): up to 16 warps, one or two CTAs per SM
+template <int Q, int MODE>
+__global__ void __launch_bounds__(512, 1) kb_stft_mc_kernel(const __grid_constant__ KbStftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_stft_mc_cta<Q, MODE>(p, kb_smem, blockIdx.x, gridDim.x);
 }
 
 template <int Q>
@@ -387,6 +395,69 @@ static int kb_launch_istft(const KbIstftParams& p, int grid, int smem, cudaStrea
     return 0;
 }
 
+
+// Tile shape of the multi-channel kernel: TF time frames x C channels = columns, FR = NW * FPW of
+// them per round.  Prefer many resident warps, full rounds, two CTAs per SM (their barriers
+// overlap), then longer tiles (less re-staging of the frame overlap).
+static bool kb_pick_mc_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int C, int with_wh, FwdCfg* out) {
+    const int FPW = 32 / Q;
+    const int sm_smem = 228 * 1024;
+    const int force_tf = kb_env_int("KAPRE_B200_MC_TF", 0);
+    const int force_nw = kb_env_int("KAPRE_B200_MC_NW", 0);
+    bool found = false;
+    FwdCfg best{};
+    double best_score = -1.0;
+    for (int NW = 1; NW <= 16; ++NW) {
+        if (force_nw && NW != force_nw) continue;
+        const int FR = NW * FPW;
+        if (FR > 32) continue;
+        for (int TF = 1; TF <= 32; ++TF) {
+            if (force_tf && TF != force_tf) continue;
+            const int ncol = TF * C;
+            const int rounds = (ncol + FR - 1) / FR;
+            if (rounds > 8) break;
+            const KbStftMcSmem L = kb_stft_mc_smem_layout(Q, n_fft, hop, TF, C, NW, with_wh);
+            if (L.total > dev.smem_optin) break;
+            if (NW * 32 < C) continue;                                // the loader gives every channel >= 1 thread
+            int bps = sm_smem / (L.total + 1024);
+            if (bps > 16 / NW) bps = 16 / NW;                         // 128 registers per thread
+            if (bps < 1) continue;
+            int warps = bps * NW;
+            const double eff = (double)ncol / (double)(rounds * FR);
+            const double score = warps * eff * 1000.0 + (bps >= 2 ? 400.0 : 0.0) + TF * 5.0 - rounds * 20.0;
+            if (score > best_score) {
+                best_score = score;
+                best = FwdCfg{TF, NW, L.total, bps};
+                found = true;
+            }
+        }
+    }
+    *out = best;
+    return found;
+}
+
+template <int Q, int MODE>
+static int kb_launch_stft_mc_qm(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    int rc = kb_set_smem(kb_stft_mc_kernel<Q, MODE>, smem);
+    if (rc) return rc;
+    KbProfScope prof(st);
+    kb_stft_mc_kernel<Q, MODE><<<grid, p.n_warps * 32, smem, st>>>(p);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+template <int Q>
+static int kb_launch_stft_mc(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    switch (p.mode) {
+        case KB_OUT_COMPLEX: return kb_launch_stft_mc_qm<Q, KB_OUT_COMPLEX>(p, grid, smem, st);
+        case KB_OUT_MAG: return kb_launch_stft_mc_qm<Q, KB_OUT_MAG>(p, grid, smem, st);
+        case KB_OUT_MAG_DB: return kb_launch_stft_mc_qm<Q, KB_OUT_MAG_DB>(p, grid, smem, st);
+        case KB_OUT_MAG_PHASE: return kb_launch_stft_mc_qm<Q, KB_OUT_MAG_PHASE>(p, grid, smem, st);
+    }
+    return kb_fail(KAPRE_E_INVALID, "bad mode for the multi-channel kernel");
+}
+
 static int kb_check_device(const DevInfo& d) {
     int cur = -1;
     KB_CUDA(cudaGetDevice(&cur));
@@ -609,29 +680,63 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     }
     if (dbmode) { p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev; }
     if (mode == KAPRE_OUT_MAG_PHASE) { p.db_on = dbmode ? 1 : 0; p.ph_off = (long long)C * od->stride_c; }
-    p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
-    const long long tiles = (long long)B * C * p.n_tiles_t;
-    if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
-    const int force_bps = kb_env_int("KAPRE_B200_BPS", 0);   // experiment: CTAs per SM (occupancy study)
-    if (force_bps > 0 && force_bps < cfg.bps) {
-        cfg.bps = force_bps;
-        const int want = (228 * 1024) / force_bps - 2048;   // pad the request so that no more CTAs fit
-        if (want > cfg.smem && want <= plan->dev.smem_optin) cfg.smem = want;
-    }
-    long long gmax = (long long)plan->dev.sm_count * cfg.bps;
-    const int grid = (int)(tiles < gmax ? tiles : gmax);
-    switch (plan->Q) {
-        case 4: rc = kb_launch_stft<4>(p, grid, cfg.smem, st); break;
-        case 8: rc = kb_launch_stft<8>(p, grid, cfg.smem, st); break;
-        case 16: rc = kb_launch_stft<16>(p, grid, cfg.smem, st); break;
-        case 32: rc = kb_launch_stft<32>(p, grid, cfg.smem, st); break;
-        default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+    // interleaved (channels_last) tensors with several channels: tiles that hold all channels
+    const bool strided_in = xd->stride_l != 1, strided_out = od->stride_f != 1;
+    const bool mc_ok = !fbmode && C > 1 && C <= 32 && (strided_in || strided_out) && xd->stride_b >= 0 &&
+                       xd->stride_c >= 0 && xd->stride_l >= 0 && kb_env_int("KAPRE_B200_NOMC", 0) == 0;
+    FwdCfg mcfg{};
+    const int mc_wh = (!plan->cosw || (plan->hop & 1)) ? 1 : 0;
+    const bool use_mc = mc_ok && kb_pick_mc_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, C, mc_wh, &mcfg);
+    long long tiles;
+    int grid;
+    if (use_mc) {
+        cfg = mcfg;
+        p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
+        p.mc_wh = mc_wh;
+        p.mc_cl_in = (xd->stride_c < xd->stride_l) ? 1 : 0;
+        p.mc_out = (od->stride_c == 1) ? 1 : 0;
+        const int FR = cfg.NW * (32 / plan->Q), ncol = cfg.TF * C;
+        const int last = ncol - ((ncol - 1) / FR) * FR;
+        p.mc_magic_c = kb_magic((unsigned)C);
+        p.mc_magic_g = kb_magic((unsigned)((cfg.NW * 32) / C));
+        p.mc_magic_fr = kb_magic((unsigned)(FR < ncol ? FR : ncol));
+        p.mc_magic_last = kb_magic((unsigned)last);
+        tiles = (long long)B * p.n_tiles_t;
+        if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
+        const long long gmax = (long long)plan->dev.sm_count * cfg.bps;
+        grid = (int)(tiles < gmax ? tiles : gmax);
+        switch (plan->Q) {
+            case 4: rc = kb_launch_stft_mc<4>(p, grid, cfg.smem, st); break;
+            case 8: rc = kb_launch_stft_mc<8>(p, grid, cfg.smem, st); break;
+            case 16: rc = kb_launch_stft_mc<16>(p, grid, cfg.smem, st); break;
+            case 32: rc = kb_launch_stft_mc<32>(p, grid, cfg.smem, st); break;
+            default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+        }
+    } else {
+        p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
+        tiles = (long long)B * C * p.n_tiles_t;
+        if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
+        const int force_bps = kb_env_int("KAPRE_B200_BPS", 0);   // experiment: CTAs per SM (occupancy study)
+        if (force_bps > 0 && force_bps < cfg.bps) {
+            cfg.bps = force_bps;
+            const int want = (228 * 1024) / force_bps - 2048;   // pad the request so that no more CTAs fit
+            if (want > cfg.smem && want <= plan->dev.smem_optin) cfg.smem = want;
+        }
+        const long long gmax = (long long)plan->dev.sm_count * cfg.bps;
+        grid = (int)(tiles < gmax ? tiles : gmax);
+        switch (plan->Q) {
+            case 4: rc = kb_launch_stft<4>(p, grid, cfg.smem, st); break;
+            case 8: rc = kb_launch_stft<8>(p, grid, cfg.smem, st); break;
+            case 16: rc = kb_launch_stft<16>(p, grid, cfg.smem, st); break;
+            case 32: rc = kb_launch_stft<32>(p, grid, cfg.smem, st); break;
+            default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+        }
     }
     if (rc) return rc;
     {
         char buf[160];
-        snprintf(buf, sizeof(buf), "Q%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld", plan->Q, cfg.TF, cfg.NW,
-                 (int)bulk, grid, cfg.smem, cfg.bps, tiles);
+        snprintf(buf, sizeof(buf), "%sQ%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld", use_mc ? "MC " : "", plan->Q,
+                 cfg.TF, cfg.NW, use_mc ? 0 : (int)bulk, grid, cfg.smem, cfg.bps, tiles);
         g_launch_info = buf;
     }
     if (dbmode) {

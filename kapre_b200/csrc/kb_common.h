@@ -91,6 +91,11 @@ struct KbStftParams {
     int TF;          // frames per tile
     int n_tiles_t;   // ceil(T / TF)
     int n_warps;     // warps per CTA
+    // multi-channel tiles (stft_mc_core.cuh): TF = time frames per tile, all C channels each
+    int mc_wh;                 // window table needed in shared memory (no in-register window, or odd hop)
+    int mc_cl_in;              // input is channel-interleaved (x_sc < x_sl): walk (sample, channel) in memory order
+    int mc_out;                // output is channel-interleaved (o_sc == 1): cooperative pair step
+    unsigned mc_magic_c, mc_magic_g, mc_magic_fr, mc_magic_last;   // kb_magic() of C, CTA size / C, columns per round (full / last)
 };
 
 struct KbIstftParams {

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../kapre_b200/csrc/kb_tables.h"
 #include "../../kapre_b200/csrc/stft_core.cuh"
+#include "../../kapre_b200/csrc/stft_mc_core.cuh"
 #include "../../kapre_b200/csrc/istft_core.cuh"
 
 template <int Q, int MODE>
@@ -30,6 +31,27 @@ static void run_stft(const KbStftParams& p, int n_cta) {
         case KB_OUT_FB: run_stft_qm<Q, KB_OUT_FB>(p, n_cta); break;
         case KB_OUT_FB_DB: run_stft_qm<Q, KB_OUT_FB_DB>(p, n_cta); break;
         case KB_OUT_MAG_PHASE: run_stft_qm<Q, KB_OUT_MAG_PHASE>(p, n_cta); break;
+    }
+}
+
+template <int Q, int MODE>
+static void run_stft_mc_qm(const KbStftParams& p, int n_cta) {
+    const KbStftMcSmem L = kb_stft_mc_smem_layout(Q, p.n_fft, p.hop, p.TF, p.C, p.n_warps, p.mc_wh);
+    std::vector<char> raw(L.total + 64 + 16);
+    char* smem = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(raw.begin(), raw.end(), (char)0x7f);
+        kb_stft_mc_cta<Q, MODE>(p, smem, cta, n_cta);
+    }
+}
+
+template <int Q>
+static void run_stft_mc(const KbStftParams& p, int n_cta) {
+    switch (p.mode) {
+        case KB_OUT_COMPLEX: run_stft_mc_qm<Q, KB_OUT_COMPLEX>(p, n_cta); break;
+        case KB_OUT_MAG: run_stft_mc_qm<Q, KB_OUT_MAG>(p, n_cta); break;
+        case KB_OUT_MAG_DB: run_stft_mc_qm<Q, KB_OUT_MAG_DB>(p, n_cta); break;
+        case KB_OUT_MAG_PHASE: run_stft_mc_qm<Q, KB_OUT_MAG_PHASE>(p, n_cta); break;
     }
 }
 
@@ -89,6 +111,53 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
         case 8: run_stft<8>(p, n_cta); break;
         case 16: run_stft<16>(p, n_cta); break;
         case 32: run_stft<32>(p, n_cta); break;
+    }
+    return 0;
+}
+
+// Multi-channel tiles (stft_mc_core.cuh): TF = time frames per tile, every tile holds all C channels.
+int kb_emu_stft_mc(const float* x, long long x_sb, long long x_sc, long long x_sl, int B, int C, int L,
+                   int n_fft, int win_length, int hop, int pad_left, int T, const float* window,
+                   int mode, void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk,
+                   float amin, float db_mul, float db_sub, unsigned int* item_max, int TF, int n_warps, int n_cta,
+                   int db_on, long long ph_off) {
+    const int Q = kb_q_for_nfft(n_fft);
+    if (!Q) return -1;
+    if (mode == KB_OUT_FB || mode == KB_OUT_FB_DB) return -2;
+    if (n_warps * (32 / Q) > 32) return -2;
+    std::vector<float> wh; std::vector<float2> twp, twn;
+    kb_make_wh(window, win_length, n_fft, wh);
+    kb_make_twp(Q, twp);
+    kb_make_twn(n_fft, twn);
+    KbStftParams p{};
+    p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
+    p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left;
+    p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data();
+    std::vector<kb_f4> cwq;
+    {
+        double ca = 0.0, cb = 0.0;
+        if (kb_fit_cosine_window(window, win_length, n_fft, &ca, &cb) && !getenv("KAPRE_B200_NOCOSW")) {
+            kb_make_cwq(Q, n_fft, cb, cwq);
+            p.cosw = 1; p.cw_a0 = (float)(0.5 * ca); p.cwq = cwq.data();
+        }
+    }
+    p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
+    p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max; p.db_on = db_on; p.ph_off = ph_off;
+    p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
+    p.mc_wh = (!p.cosw || (hop & 1)) ? 1 : 0;
+    p.mc_cl_in = (x_sc < x_sl) ? 1 : 0;
+    p.mc_out = (o_sc == 1) ? 1 : 0;
+    const int FR = n_warps * (32 / Q), ncol = TF * C;
+    const int last = ncol - ((ncol - 1) / FR) * FR;
+    p.mc_magic_c = kb_magic((unsigned)C);
+    p.mc_magic_g = kb_magic((unsigned)((n_warps * 32) / C));
+    p.mc_magic_fr = kb_magic((unsigned)(FR < ncol ? FR : ncol));
+    p.mc_magic_last = kb_magic((unsigned)last);
+    switch (Q) {
+        case 4: run_stft_mc<4>(p, n_cta); break;
+        case 8: run_stft_mc<8>(p, n_cta); break;
+        case 16: run_stft_mc<16>(p, n_cta); break;
+        case 32: run_stft_mc<32>(p, n_cta); break;
     }
     return 0;
 }

@@ -99,3 +99,52 @@ def test_emu_istft(n_fft, hop, win, TFc, nw, ifmt, ofmt):
     y = E.emu_istft(X, n_fft, win, hop, dual, ifmt, ofmt, TFc=TFc, n_warps=nw, n_cta=2)
     assert y.shape == ref.shape
     assert nerr(y, ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------- multi-channel tiles
+@pytest.mark.parametrize('n_fft,hop,win,C,TF,nw', [(2048, 1024, 2048, 6, 1, 6), (2048, 1024, 2048, 6, 2, 4),
+                                                  (1024, 256, 1024, 2, 8, 8), (512, 128, 400, 3, 3, 2),
+                                                  (256, 64, 256, 5, 4, 3), (1024, 255, 1024, 2, 2, 1),
+                                                  (512, 256, 512, 4, 5, 4)])
+@pytest.mark.parametrize('ifmt', ['channels_last', 'channels_first'])
+@pytest.mark.parametrize('ofmt', ['channels_last', 'channels_first'])
+def test_emu_mc_complex_and_mag(n_fft, hop, win, C, TF, nw, ifmt, ofmt):
+    """stft_mc_core.cuh: all-channel tiles, de-interleaving loader, cooperative (interleaved output)
+    and per-warp (planar output) pair step; odd hop exercises the scalar window path."""
+    rng = np.random.default_rng(n_fft + hop + C)
+    x = wave(rng, 2, C, 7003, ifmt)
+    w = O.get_window(None, win).astype(np.float32)
+    for pads in ((False, False), (True, True)):
+        ref = O.stft_layer(x, n_fft, win, hop, None, pads[0], pads[1], ifmt, ofmt)
+        out, _ = E.emu_stft_mc(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_COMPLEX, ifmt, ofmt, TF=TF, n_warps=nw)
+        assert out.shape == ref.shape
+        assert not np.isnan(out).any()
+        assert nerr(out, ref) < 1e-6
+    mag, _ = E.emu_stft_mc(x, n_fft, win, hop, w, True, False, E.MODE_MAG, ifmt, ofmt, TF=TF, n_warps=nw, n_cta=5)
+    ref = O.stft_layer(x, n_fft, win, hop, None, True, False, ifmt, ofmt)
+    assert nerr(mag, np.abs(ref)) < 1e-6
+
+
+@pytest.mark.parametrize('fmt', ['channels_last', 'channels_first'])
+def test_emu_mc_db_and_phase(fmt):
+    rng = np.random.default_rng(5)
+    B, C = 3, 6
+    x = wave(rng, B, C, 9000, fmt)
+    x[1] *= 1e-3
+    w = O.get_window('hamming_window', 2048).astype(np.float32)
+    spec = O.stft_layer(x, 2048, 2048, 1024, 'hamming_window', False, True, fmt, fmt)
+    mag = np.abs(spec)
+    out, item_max = E.emu_stft_mc(x, 2048, 2048, 1024, w, False, True, E.MODE_MAG_DB, fmt, fmt, TF=1, n_warps=6)
+    ref_db = 10.0 * np.log10(np.maximum(mag, 1e-5))       # un-clamped: the clamp is a second kernel
+    assert np.abs(out - ref_db).max() < 1e-3     # fp32 FFT round-off on the weakest bins of the 1e-3-scaled item
+    want_max = np.maximum(mag, 1e-5).reshape(B, -1).max(axis=1)
+    assert np.allclose(item_max, want_max, rtol=2e-6)
+    both, item_max = E.emu_stft_mc(x, 2048, 2048, 1024, w, False, True, E.MODE_MAG_PHASE, fmt, fmt, TF=2, n_warps=4,
+                                   db_on=1)
+    ch_axis = 3 if fmt == 'channels_last' else 1
+    m, ph = np.split(both, 2, axis=ch_axis)
+    assert np.abs(m - ref_db).max() < 1e-3
+    ok = mag > 1e-3 * mag.max()
+    d = np.abs(np.angle(np.exp(1j * (ph - np.angle(spec)))))
+    assert d[ok].max() < 1e-4
+    assert np.allclose(item_max, want_max, rtol=2e-6)

@@ -204,3 +204,31 @@ def test_oracle_delta_frame_energy_known_answers():
     en = O.energy_layer(np.ones((1, 8, 1)), sample_rate=4, ref_duration=1.0, frame_length=4, hop_length=4,
                         data_format='channels_last')
     np.testing.assert_allclose(en.ravel(), [4.0, 4.0])
+
+
+def test_predict_result_buffers_are_recycled_only_when_released(monkeypatch):
+    """Sequential.predict hands out page-locked result buffers from a pool; a buffer may be reused only
+    after the array returned for it (and every view of it) is gone."""
+    import torch
+    import kapre_b200.composed as C
+    real_empty = torch.empty
+
+    def cpu_empty(*a, **k):          # no CUDA in this tier: drop the pinning request
+        k.pop('pin_memory', None)
+        return real_empty(*a, **k)
+    monkeypatch.setattr(torch, 'empty', cpu_empty)
+    seq = C.Sequential([])
+
+    def get():
+        return seq._pinned_result((4, 5), torch.float32)[1]
+    n1, n2 = get(), get()
+    assert n1.ctypes.data != n2.ctypes.data
+    p1 = n1.ctypes.data
+    view = n1[1:3]
+    del n1
+    n3 = get()
+    assert n3.ctypes.data not in (p1, n2.ctypes.data)     # the view still pins buffer 1
+    del view
+    n4 = get()
+    assert n4.ctypes.data == p1                           # released -> recycled, no new allocation
+    assert len(seq._result_pool) == 3

@@ -61,6 +61,34 @@ def main():
         t = timeit(lambda: layer.predict(xh, batch_size=bs), n=8)
         res['predict_chunks_%d_ms' % chunks] = t * 1e3
         res['predict_chunks_%d_fps' % chunks] = frames / t
+    # the bench's pattern: alternate two pinned inputs, keep the previous result alive
+    xh2 = torch.empty_like(xh).pin_memory()
+    xh2.copy_(xh)
+    ins = [xh, xh2]
+    for i in range(4):
+        keep = layer.predict(ins[i % 2])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(20):
+        keep = layer.predict(ins[i % 2])
+    torch.cuda.synchronize()
+    t = (time.perf_counter() - t0) / 20
+    res['predict_bench_pattern_ms'] = t * 1e3
+    t0 = time.perf_counter()
+    for i in range(20):
+        layer.predict(ins[i % 2])
+    torch.cuda.synchronize()
+    t = (time.perf_counter() - t0) / 20
+    res['predict_discard_result_ms'] = t * 1e3
+    import cProfile, pstats, io
+    pr = cProfile.Profile()
+    pr.enable()
+    for i in range(10):
+        keep = layer.predict(ins[i % 2])
+    pr.disable()
+    sio = io.StringIO()
+    pstats.Stats(pr, stream=sio).sort_stats('cumulative').print_stats(14)
+    res['profile'] = sio.getvalue().splitlines()[:40]
     print(json.dumps(res, indent=1))
 
 
