@@ -20,7 +20,7 @@ from .backend import _CH_DEFAULT_STR, _CH_FIRST_STR, _CH_LAST_STR
 from .time_frequency import (STFT, ApplyFilterbank, InverseSTFT, Layer, Magnitude, MagnitudeToDecibel, Phase,
                              get_registered_object)
 
-__all__ = ['Sequential', 'StftMagPhase', 'get_stft_magnitude_layer', 'get_melspectrogram_layer',
+__all__ = ['CapturedSequential', 'Sequential', 'StftMagPhase', 'get_stft_magnitude_layer', 'get_melspectrogram_layer',
            'get_log_frequency_spectrogram_layer', 'get_perfectly_reconstructing_stft_istft', 'get_stft_mag_phase']
 
 
@@ -160,6 +160,12 @@ class Sequential(Layer):
         s_out.synchronize()
         return out_arr
 
+    def capture(self, example):
+        """Freeze this model for one input shape into a CUDA graph (``CapturedSequential``): replaying it
+        costs one graph launch instead of one kernel launch + Python / ctypes dispatch per layer, which is
+        what bounds small batches (cfg1: 13 us of kernel under ~40 us of submission)."""
+        return CapturedSequential(self, example)
+
     # -- serialisation ------------------------------------------------------------------------
     def get_config(self):
         return {'name': self.name,
@@ -176,6 +182,43 @@ class Sequential(Layer):
                 raise ValueError('Unknown layer class %r' % (item['class_name'],))
             layers.append(klass.from_config(dict(item['config'])))
         return cls(layers, name=config.get('name'))
+
+
+class CapturedSequential:
+    """A ``Sequential`` captured into a CUDA graph for a fixed input shape / dtype / device.
+
+    ``captured(x)`` copies ``x`` (host or device) into the graph's static input, replays the graph and
+    returns the static output tensor (valid until the next call; ``.clone()`` it to keep it).  The
+    kernels are the same C-ABI launches as in eager mode, recorded once on a private stream."""
+
+    def __init__(self, model, example):
+        ops._require_cuda()
+        x, _ = ops.to_device(example)
+        self.model = model
+        self.static_in = x.clone()
+        cur = torch.cuda.current_stream()
+        self._stream = torch.cuda.Stream(device=x.device)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):      # warm-up on the capture stream: plans, workspace, smem attrs
+            for _ in range(2):
+                model.call(self.static_in)
+        self._stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self._stream):
+            self.static_out = model.call(self.static_in)
+        cur.wait_stream(self._stream)
+
+    def __call__(self, x):
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if tuple(x.shape) != tuple(self.static_in.shape):
+            raise ValueError('captured for input shape %s, got %s' % (tuple(self.static_in.shape), tuple(x.shape)))
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+    def predict(self, x, **kwargs):
+        return ops.to_host(self(x))
 
 
 def get_stft_magnitude_layer(input_shape=None, n_fft=2048, win_length=None, hop_length=None, window_name=None,

@@ -497,3 +497,22 @@ def test_logmel_to_mfcc(K, fmt):
     ref = O.logmel_to_mfcc(O.melspectrogram_layer(x, output_data_format=fmt, **kw), 13, fmt)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() < 5e-4
+
+
+def test_cuda_graph_capture_matches_eager(K):
+    """Sequential.capture: the same kernels recorded into a CUDA graph; replays with new inputs must equal
+    the eager path bit for bit (cfg1 shape: log-mel with the fused dB clamp)."""
+    rng = np.random.default_rng(11)
+    layer = K.get_melspectrogram_layer(n_fft=512, hop_length=256, sample_rate=16000, n_mels=64, return_decibel=True,
+                                       input_data_format='channels_last', output_data_format='channels_last')
+    x0 = torch.from_numpy(rng.uniform(-1, 1, size=(4, 16000, 1)).astype(np.float32)).cuda()
+    cap = layer.capture(x0)
+    for scale in (1.0, 1e-3, 0.3):
+        x = torch.from_numpy((scale * rng.uniform(-1, 1, size=(4, 16000, 1))).astype(np.float32)).cuda()
+        want = layer(x)
+        got = cap(x).clone()
+        assert torch.equal(got, want)
+    got_host = cap.predict(x.cpu().numpy())
+    assert np.array_equal(got_host, want.cpu().numpy())
+    with pytest.raises(ValueError):
+        cap(torch.zeros((2, 16000, 1), device='cuda'))
