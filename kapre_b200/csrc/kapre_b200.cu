@@ -75,6 +75,12 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel(const __g
     kb_stft_cta<Q, MODE>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
+template <int Q, int MODE>
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_mcfb_kernel(const __grid_constant__ KbStftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_stft_mcfb_cta<Q, MODE>(p, kb_smem, blockIdx.x, gridDim.x);
+}
+
 // multi-channel tiles (interleaved tensors): up to 16 warps, one or two CTAs per SM
 template <int Q, int MODE>
 __global__ void __launch_bounds__(512, 1) kb_stft_mc_kernel(const __grid_constant__ KbStftParams p) {
@@ -436,6 +442,51 @@ static bool kb_pick_mc_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int C,
     return found;
 }
 
+// Filterbank modes on all-channel tiles: one round per tile, TF = floor(NW * FPW / C) time frames.
+static bool kb_pick_mcfb_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int C, int with_wh, int n_bands,
+                             int n_chunks, FwdCfg* out) {
+    const int FPW = 32 / Q;
+    const int sm_smem = 228 * 1024;
+    bool found = false;
+    FwdCfg best{};
+    double best_score = -1.0;
+    const int nws[3] = {2, 4, 8};
+    for (int a = 0; a < 3; ++a) {
+        const int NW = nws[a];
+        const int FR = NW * FPW;
+        if (FR > 32 || FR < C || NW * 32 < C) continue;
+        const int TF = FR / C;
+        const KbStftMcFbSmem L = kb_stft_mcfb_smem_layout(Q, n_fft, hop, TF, C, NW, with_wh, n_bands, n_chunks);
+        if (L.total > dev.smem_optin) continue;
+        int bps = sm_smem / (L.total + 1024);
+        if (bps > 16 / NW) bps = 16 / NW;
+        if (bps < 1) continue;
+        const double eff = (double)(TF * C) / (double)FR;
+        const double score = bps * NW * eff * 1000.0 + TF * 10.0 + NW;
+        if (score > best_score) { best_score = score; best = FwdCfg{TF, NW, L.total, bps}; found = true; }
+    }
+    *out = best;
+    return found;
+}
+
+template <int Q, int MODE>
+static int kb_launch_stft_mcfb_qm(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    int rc = kb_set_smem(kb_stft_mcfb_kernel<Q, MODE>, smem);
+    if (rc) return rc;
+    KbProfScope prof(st);
+    kb_stft_mcfb_kernel<Q, MODE><<<grid, p.n_warps * 32, smem, st>>>(p);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+template <int Q>
+static int kb_launch_stft_mcfb(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    if (p.mode == KB_OUT_FB) return kb_launch_stft_mcfb_qm<Q, KB_OUT_FB>(p, grid, smem, st);
+    if (p.mode == KB_OUT_FB_DB) return kb_launch_stft_mcfb_qm<Q, KB_OUT_FB_DB>(p, grid, smem, st);
+    return kb_fail(KAPRE_E_INVALID, "bad mode for the multi-channel filterbank kernel");
+}
+
 template <int Q, int MODE>
 static int kb_launch_stft_mc_qm(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
     int rc = kb_set_smem(kb_stft_mc_kernel<Q, MODE>, smem);
@@ -682,11 +733,13 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if (mode == KAPRE_OUT_MAG_PHASE) { p.db_on = dbmode ? 1 : 0; p.ph_off = (long long)C * od->stride_c; }
     // interleaved (channels_last) tensors with several channels: tiles that hold all channels
     const bool strided_in = xd->stride_l != 1, strided_out = od->stride_f != 1;
-    const bool mc_ok = !fbmode && C > 1 && C <= 32 && (strided_in || strided_out) && xd->stride_b >= 0 &&
+    const bool mc_ok = C > 1 && C <= 32 && (strided_in || strided_out) && xd->stride_b >= 0 &&
                        xd->stride_c >= 0 && xd->stride_l >= 0 && kb_env_int("KAPRE_B200_NOMC", 0) == 0;
     FwdCfg mcfg{};
     const int mc_wh = (!plan->cosw || (plan->hop & 1)) ? 1 : 0;
-    const bool use_mc = mc_ok && kb_pick_mc_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, C, mc_wh, &mcfg);
+    const bool use_mc = mc_ok && (fbmode ? kb_pick_mcfb_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, C, mc_wh,
+                                                            fb->n_bands, fb->n_chunks, &mcfg)
+                                         : kb_pick_mc_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, C, mc_wh, &mcfg));
     long long tiles;
     int grid;
     if (use_mc) {
@@ -705,12 +758,22 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
         const long long gmax = (long long)plan->dev.sm_count * cfg.bps;
         grid = (int)(tiles < gmax ? tiles : gmax);
-        switch (plan->Q) {
-            case 4: rc = kb_launch_stft_mc<4>(p, grid, cfg.smem, st); break;
-            case 8: rc = kb_launch_stft_mc<8>(p, grid, cfg.smem, st); break;
-            case 16: rc = kb_launch_stft_mc<16>(p, grid, cfg.smem, st); break;
-            case 32: rc = kb_launch_stft_mc<32>(p, grid, cfg.smem, st); break;
-            default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+        if (fbmode) {
+            switch (plan->Q) {
+                case 4: rc = kb_launch_stft_mcfb<4>(p, grid, cfg.smem, st); break;
+                case 8: rc = kb_launch_stft_mcfb<8>(p, grid, cfg.smem, st); break;
+                case 16: rc = kb_launch_stft_mcfb<16>(p, grid, cfg.smem, st); break;
+                case 32: rc = kb_launch_stft_mcfb<32>(p, grid, cfg.smem, st); break;
+                default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+            }
+        } else {
+            switch (plan->Q) {
+                case 4: rc = kb_launch_stft_mc<4>(p, grid, cfg.smem, st); break;
+                case 8: rc = kb_launch_stft_mc<8>(p, grid, cfg.smem, st); break;
+                case 16: rc = kb_launch_stft_mc<16>(p, grid, cfg.smem, st); break;
+                case 32: rc = kb_launch_stft_mc<32>(p, grid, cfg.smem, st); break;
+                default: rc = kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+            }
         }
     } else {
         p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;

@@ -433,3 +433,358 @@ __device__ __forceinline__ void kb_stft_mc_cta(const KbStftParams& p, char* smem
         }
     }
 }
+
+// ==========================================================================================
+// Filterbank modes (mel / log-frequency, optional dB) on all-channel tiles.
+//
+// Same tile decomposition and loader as above; one round per tile (NCOL = TF * C <= NW * FPW columns),
+// then the filterbank epilogue of stft_core.cuh: magnitudes parked in the warps' exchange regions as
+// [bin][frame-in-warp], 32 lane groups walk the chunk lists, results staged in out_s[column][band].
+// The copy-out is what changes: for interleaved outputs a warp writes one time frame's (band, channel)
+// block, which is contiguous in memory, instead of one channel's bands C floats apart.
+// ==========================================================================================
+struct KbStftMcFbSmem {
+    int wh, twp, twn, cwq, cw, cm, cg, samples, outs, ex, total;
+    int span, spanp, exw, Mp;
+};
+
+KB_HD KbStftMcFbSmem kb_stft_mcfb_smem_layout(int Q, int n_fft, int hop, int TFt, int C, int n_warps, int with_wh,
+                                              int n_bands, int n_chunks) {
+    KbStftMcFbSmem s;
+    const int P = 32 * Q, FPW = 32 / Q;
+    const KbStftMcSmem base = kb_stft_mc_smem_layout(Q, n_fft, hop, TFt, C, n_warps, with_wh);
+    int off = 0;
+    s.wh = off;  if (with_wh) off += kb_align16(n_fft * 4);
+    s.twp = off; off += kb_align16(Q * 33 * 8);
+    s.twn = off; off += kb_align16((P / 2) * 8);
+    s.cwq = off; off += Q * 16;
+    s.cw = off;  off += n_chunks * 16;
+    s.cm = off;  off += kb_align16(n_chunks * 8);
+    s.cg = off;  off += kb_align16(33 * 4);
+    s.span = base.span; s.spanp = base.spanp;
+    s.samples = off; off += kb_align16(C * s.spanp * 4);
+    s.Mp = n_bands | 1;
+    s.outs = off; off += kb_align16(n_warps * FPW * s.Mp * 4);
+    s.exw = kb_exw(Q);            // geometry of stft_core.cuh: its filterbank phase is reused unchanged
+    s.ex = off;  off += kb_align16(n_warps * s.exw * 8);
+    s.total = off;
+    return s;
+}
+
+template <int Q, int MODE>
+#if defined(KB_HOST_EMU)
+inline void kb_stft_mcfb_cta(const KbStftParams& p, char* smem, int cta, int n_cta)
+#else
+__device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* smem, int cta, int n_cta)
+#endif
+{
+    constexpr int P = 32 * Q;
+    constexpr int FPW = 32 / Q;
+    constexpr int ZSTR = P + Q;
+    constexpr bool dbmode = (MODE == KB_OUT_FB_DB);
+    const int NW = p.n_warps;
+    const int kb_nt = NW * 32;
+    (void)kb_nt;
+    const int H = p.hop, N = p.n_fft, C = p.C, TFt = p.TF;
+    const int NCOL = TFt * C;                       // <= NW * FPW (host guarantees)
+    const KbStftMcFbSmem L = kb_stft_mcfb_smem_layout(Q, N, H, TFt, C, NW, p.mc_wh, p.n_bands, p.n_chunks);
+    float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
+    cpx* __restrict__ twp_s = reinterpret_cast<cpx*>(smem + L.twp);
+    cpx* __restrict__ twn_s = reinterpret_cast<cpx*>(smem + L.twn);
+    kb_f4* __restrict__ cwq_s = reinterpret_cast<kb_f4*>(smem + L.cwq);
+    kb_f4* __restrict__ cw_s = reinterpret_cast<kb_f4*>(smem + L.cw);
+    kb_i2* __restrict__ cm_s = reinterpret_cast<kb_i2*>(smem + L.cm);
+    int* __restrict__ cg_s = reinterpret_cast<int*>(smem + L.cg);
+    float* smp = reinterpret_cast<float*>(smem + L.samples);
+    float* __restrict__ out_s = reinterpret_cast<float*>(smem + L.outs);
+    cpx* ex_s = reinterpret_cast<cpx*>(smem + L.ex);
+    const int EXS = L.exw;
+    const int n_tiles = p.B * p.n_tiles_t;
+    const int span = L.span, spanp = L.spanp;
+    const bool even_base = (H & 1) == 0;
+    const bool use_cosw = even_base && p.cosw;
+
+#if defined(KB_HOST_EMU)
+    std::vector<KbThreadRegs> kb_regs(kb_nt);
+#else
+    KbThreadRegs kb_regs;
+#endif
+
+    KB_PHASE_BEGIN
+        (void)R;
+        if (p.mc_wh) { for (int i = tid; i < N; i += kb_nt) wh_s[i] = p.wh[i]; }
+        for (int i = tid; i < Q * 33; i += kb_nt) { float2 t = p.twp[i]; twp_s[i] = cmake(t.x, t.y); }
+        for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
+        if (p.cosw) { for (int i = tid; i < Q; i += kb_nt) cwq_s[i] = p.cwq[i]; }
+        for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
+        for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.cg[i];
+    KB_PHASE_END
+    KB_SYNC_CTA;
+    if (cta < n_tiles) {
+        const int b0 = cta / p.n_tiles_t;
+        KB_PHASE_BEGIN
+            (void)R;
+            kb_mc_issue_loads(p, smp, b0, (cta - b0 * p.n_tiles_t) * TFt, span, spanp, tid, kb_nt);
+        KB_PHASE_END
+    }
+
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+        const int b = tile / p.n_tiles_t;
+        const int t0 = (tile - b * p.n_tiles_t) * TFt;
+        const bool has_next = (tile + n_cta) < n_tiles;
+        const int nb = (tile + n_cta) / p.n_tiles_t;
+        const int nt0 = ((tile + n_cta) - nb * p.n_tiles_t) * TFt;
+
+        KB_PHASE_BEGIN
+            (void)tid;
+            R.runmax = 0.0f;
+            kb_cp_async_wait();
+        KB_PHASE_END
+        KB_SYNC_CTA;      // samples visible; the previous tile's copy-out is done with out_s
+
+        // ---- phase 1: window, 32-point DFTs, twiddle, transpose-store ---------------------------
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            const int g = lane / Q, q = lane % Q;
+            const int col = warp * FPW + g;
+            if (col < NCOL) {
+                const int fl = kb_fdiv(col, C, p.mc_magic_c), ch = col - fl * C;
+                const float* fr = smp + ch * spanp + fl * H;
+                if (use_cosw) {
+                    const kb_f4 cq = cwq_s[q];
+                    const cpx cc = cmake(cq.x, cq.y), ss = cmake(cq.z, cq.w);
+                    const cpx a0 = cmake(p.cw_a0, p.cw_a0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n2 = 2 * (q + Q * j);
+                        const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
+                        const float cj = j <= 16 ? kb_cos32(j) : kb_cos32(32 - j);
+                        const float sj = j <= 16 ? kb_sin32(j) : -kb_sin32(32 - j);
+                        cpx wv = a0;
+                        if (cj != 0.0f) wv = cfma_s(cc, -cj, wv);
+                        if (sj != 0.0f) wv = cfma_s(ss, sj, wv);
+                        R.v[j] = cmul_elem(xv, wv);
+                    }
+                } else if (even_base) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n2 = 2 * (q + Q * j);
+                        const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
+                        const cpx wv = *reinterpret_cast<const cpx*>(wh_s + n2);
+                        R.v[j] = cmul_elem(xv, wv);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n2 = 2 * (q + Q * j);
+                        R.v[j] = cmake(fr[n2] * wh_s[n2], fr[n2 + 1] * wh_s[n2 + 1]);
+                    }
+                }
+                kb_fft_dif<32>(R.v);
+                cpx* ex = ex_s + warp * EXS + (g * Q + q) * 33;
+                const cpx* tw = twp_s + q * 33;
+                ex[0] = R.v[0];
+#pragma unroll
+                for (int k1 = 1; k1 < 32; ++k1) ex[k1] = cmul(R.v[kb_brev<32>(k1)], tw[k1]);
+            }
+        KB_PHASE_END
+        KB_SYNC_WARP;
+        // ---- phase 2: gather this lane's columns ----------------------------------------------
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            const int g = lane / Q, q = lane % Q;
+            if (warp * FPW + g < NCOL) {
+                const cpx* ex = ex_s + warp * EXS + (g * Q) * 33;
+#pragma unroll
+                for (int i = 0; i < FPW; ++i) {
+                    const int k1 = q + Q * i;
+#pragma unroll
+                    for (int q2 = 0; q2 < Q; ++q2) R.v[i * Q + q2] = ex[q2 * 33 + k1];
+                }
+            }
+        KB_PHASE_END
+        KB_SYNC_WARP;
+        // ---- phase 3: Q-point DFTs, natural-order store ---------------------------------------
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            const int g = lane / Q, q = lane % Q;
+            if (warp * FPW + g < NCOL) {
+                cpx* zs = ex_s + warp * EXS + g * ZSTR;
+#pragma unroll
+                for (int i = 0; i < FPW; ++i) {
+                    kb_fft_dif<Q>(R.v + i * Q);
+                    const int k1 = q + Q * i;
+#pragma unroll
+                    for (int k2 = 0; k2 < Q; ++k2) zs[k1 + 32 * k2] = R.v[i * Q + kb_brev<Q>(k2)];
+                }
+            }
+        KB_PHASE_END
+        KB_SYNC_WARP;
+        // ---- phase 4: pair step, magnitudes parked in registers (R.v is dead) -------------------
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            float* magr = reinterpret_cast<float*>(R.v);
+#pragma unroll
+            for (int gg = 0; gg < FPW; ++gg) {
+                const bool active = (warp * FPW + gg) < NCOL;
+                const cpx* zf = ex_s + warp * EXS + gg * ZSTR;
+#pragma unroll
+                for (int i = 0; i <= Q / 2; ++i) {
+                    float m1 = 0.0f, m2 = 0.0f;
+                    if (active) {
+                        cpx X1, X2;
+                        if (i < Q / 2) {
+                            const int k = lane + 32 * i;
+                            const cpx A = zf[k];
+                            const cpx Bv = zf[(P - k) & (P - 1)];
+                            const cpx W = twn_s[k];
+                            const cpx E = cadd_conj(A, Bv);
+                            const cpx D = csub_conj(A, Bv);
+                            const cpx T = cmul(cmake(D.im, -D.re), W);
+                            X1 = cadd(E, T);
+                            X2 = csub(E, T);
+                        } else {
+                            const cpx A = zf[P / 2];
+                            X1 = cmake(2.0f * A.re, -2.0f * A.im);
+                            X2 = X1;
+                        }
+                        m1 = kb_sqrt(cnorm(X1));
+                        m2 = kb_sqrt(cnorm(X2));
+                    }
+                    magr[(gg * (Q / 2 + 1) + i) * 2 + 0] = m1;
+                    magr[(gg * (Q / 2 + 1) + i) * 2 + 1] = m2;
+                }
+            }
+        KB_PHASE_END
+        KB_SYNC_WARP;
+        // ---- phase 4b: magnitudes -> own exchange region, layout [bin][frame-in-warp] -----------
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            const float* magr = reinterpret_cast<const float*>(R.v);
+            float* mw = reinterpret_cast<float*>(ex_s + warp * EXS);
+#pragma unroll
+            for (int i = 0; i < Q / 2; ++i) {
+                const int k = lane + 32 * i;
+                float lo[FPW], hi[FPW];
+#pragma unroll
+                for (int gg = 0; gg < FPW; ++gg) {
+                    lo[gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 0];
+                    hi[gg] = magr[(gg * (Q / 2 + 1) + i) * 2 + 1];
+                }
+                kb_store_vec<FPW>(mw + k * FPW, lo);
+                kb_store_vec<FPW>(mw + (P - k) * FPW, hi);
+            }
+            if (lane == 0) {
+                float mid[FPW];
+#pragma unroll
+                for (int gg = 0; gg < FPW; ++gg) mid[gg] = magr[(gg * (Q / 2 + 1) + Q / 2) * 2 + 0];
+                kb_store_vec<FPW>(mw + (P / 2) * FPW, mid);
+            }
+            if (lane < 3) {
+#pragma unroll
+                for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;   // pad bins
+            }
+        KB_PHASE_END
+        KB_SYNC_CTA;      // all magnitudes visible; the sample planes are free
+        if (has_next) {
+            KB_PHASE_BEGIN
+                (void)R;
+                kb_mc_issue_loads(p, smp, nb, nt0, span, spanp, tid, kb_nt);
+            KB_PHASE_END
+        }
+        // ---- phase 5: filterbank (as in stft_core.cuh) ---------------------------------------------
+        KB_PHASE_BEGIN
+            (void)R;
+            const int warp = tid >> 5, lane = tid & 31;
+            const int w = lane % NW;
+            const int grp = warp * (32 / NW) + lane / NW;           // 0..31
+            const float* __restrict__ mw = reinterpret_cast<const float*>(ex_s + w * EXS);
+            float* __restrict__ ocol = out_s + (w * FPW) * L.Mp;
+            float a0[FPW], a1[FPW];
+#pragma unroll
+            for (int g = 0; g < FPW; ++g) { a0[g] = 0.0f; a1[g] = 0.0f; }
+            const int ce = cg_s[grp + 1];
+            for (int i = cg_s[grp]; i < ce; ++i) {
+                const kb_f4 wv = cw_s[i];
+                const kb_i2 mt = cm_s[i];
+                const float* mp = mw + mt.x * FPW;
+                float m01[2 * FPW], m23[2 * FPW];
+                kb_load_vec<2 * FPW>(m01, mp);
+                kb_load_vec<2 * FPW>(m23, mp + 2 * FPW);
+#pragma unroll
+                for (int g = 0; g < FPW; ++g) {
+                    a0[g] += wv.x * m01[g];
+                    a1[g] += wv.y * m01[FPW + g];
+                    a0[g] += wv.z * m23[g];
+                    a1[g] += wv.w * m23[FPW + g];
+                }
+                if (mt.y >= 0) {
+#pragma unroll
+                    for (int g = 0; g < FPW; ++g) {
+                        ocol[g * L.Mp + mt.y] = a0[g] + a1[g];
+                        a0[g] = 0.0f;
+                        a1[g] = 0.0f;
+                    }
+                }
+            }
+        KB_PHASE_END
+        KB_SYNC_CTA;
+        // ---- phase 6: decibel + copy-out ------------------------------------------------------------
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            float* o = reinterpret_cast<float*>(p.out) + (long long)b * p.o_sb;
+            const int M = p.n_bands;
+            const float amin = p.amin, dmul = p.db_mul, dsub = p.db_sub;
+            float rmax = R.runmax;
+            if (p.mc_out) {
+                // interleaved output: one time frame's (band, channel) block is contiguous
+                const int MC = M * C;
+                for (int fl = warp; fl < TFt; fl += NW) {
+                    const int t = t0 + fl;
+                    if (t >= p.T) break;
+                    float* __restrict__ orow = o + (long long)t * p.o_st;
+                    const float* __restrict__ srow = out_s + (fl * C) * L.Mp;
+                    for (int e = lane; e < MC; e += 32) {
+                        const int m = kb_fdiv(e, C, p.mc_magic_c), c = e - m * C;
+                        float v = srow[c * L.Mp + m];
+                        if (dbmode) {
+                            v = fmaxf(v, amin);
+                            rmax = fmaxf(rmax, v);
+                            v = dmul * kb_log2(v) - dsub;
+                        }
+                        orow[e] = v;
+                    }
+                }
+            } else {
+                const int sk = (int)p.o_sk;
+                for (int col = warp; col < NCOL; col += NW) {
+                    const int fl = kb_fdiv(col, C, p.mc_magic_c), c = col - fl * C;
+                    const int t = t0 + fl;
+                    if (t >= p.T) break;
+                    float* __restrict__ orow = o + (long long)c * p.o_sc + (long long)t * p.o_st;
+                    const float* __restrict__ srow = out_s + col * L.Mp;
+                    for (int m = lane; m < M; m += 32) {
+                        float v = srow[m];
+                        if (dbmode) {
+                            v = fmaxf(v, amin);
+                            rmax = fmaxf(rmax, v);
+                            v = dmul * kb_log2(v) - dsub;
+                        }
+                        orow[(long long)m * sk] = v;
+                    }
+                }
+            }
+            R.runmax = rmax;
+        KB_PHASE_END
+
+        if (dbmode) {
+#if defined(KB_HOST_EMU)
+            for (int tid = 0; tid < kb_nt; ++tid)
+                kb_atomic_max_u32(p.item_max + b, kb_f2u(kb_regs[tid].runmax));
+#else
+            const unsigned int wm = __reduce_max_sync(0xffffffffu, kb_f2u(kb_regs.runmax));
+            if ((threadIdx.x & 31) == 0 && wm != 0u) kb_atomic_max_u32(p.item_max + b, wm);
+#endif
+        }
+    }
+}

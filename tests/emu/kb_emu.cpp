@@ -45,9 +45,23 @@ static void run_stft_mc_qm(const KbStftParams& p, int n_cta) {
     }
 }
 
+template <int Q, int MODE>
+static void run_stft_mcfb_qm(const KbStftParams& p, int n_cta) {
+    const KbStftMcFbSmem L = kb_stft_mcfb_smem_layout(Q, p.n_fft, p.hop, p.TF, p.C, p.n_warps, p.mc_wh, p.n_bands,
+                                                      p.n_chunks);
+    std::vector<char> raw(L.total + 64 + 16);
+    char* smem = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(raw.begin(), raw.end(), (char)0x7f);
+        kb_stft_mcfb_cta<Q, MODE>(p, smem, cta, n_cta);
+    }
+}
+
 template <int Q>
 static void run_stft_mc(const KbStftParams& p, int n_cta) {
     switch (p.mode) {
+        case KB_OUT_FB: run_stft_mcfb_qm<Q, KB_OUT_FB>(p, n_cta); break;
+        case KB_OUT_FB_DB: run_stft_mcfb_qm<Q, KB_OUT_FB_DB>(p, n_cta); break;
         case KB_OUT_COMPLEX: run_stft_mc_qm<Q, KB_OUT_COMPLEX>(p, n_cta); break;
         case KB_OUT_MAG: run_stft_mc_qm<Q, KB_OUT_MAG>(p, n_cta); break;
         case KB_OUT_MAG_DB: run_stft_mc_qm<Q, KB_OUT_MAG_DB>(p, n_cta); break;
@@ -120,12 +134,15 @@ int kb_emu_stft_mc(const float* x, long long x_sb, long long x_sc, long long x_s
                    int n_fft, int win_length, int hop, int pad_left, int T, const float* window,
                    int mode, void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk,
                    float amin, float db_mul, float db_sub, unsigned int* item_max, int TF, int n_warps, int n_cta,
-                   int db_on, long long ph_off) {
+                   int db_on, long long ph_off, const float* fb, int n_freq, int n_bands) {
     const int Q = kb_q_for_nfft(n_fft);
     if (!Q) return -1;
-    if (mode == KB_OUT_FB || mode == KB_OUT_FB_DB) return -2;
+    const bool fbm = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
+    if (fbm && (!fb || TF * C > n_warps * (32 / Q) || (32 % n_warps) != 0)) return -2;   // kernel contract
     if (n_warps * (32 / Q) > 32) return -2;
     std::vector<float> wh; std::vector<float2> twp, twn;
+    std::vector<kb_f4> cw; std::vector<kb_i2> cm; std::vector<int> cg;
+    if (fbm) kb_make_fb_chunks(fb, n_freq, n_bands, 32, cw, cm, cg);
     kb_make_wh(window, win_length, n_fft, wh);
     kb_make_twp(Q, twp);
     kb_make_twn(n_fft, twn);
@@ -143,6 +160,7 @@ int kb_emu_stft_mc(const float* x, long long x_sb, long long x_sc, long long x_s
     }
     p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
     p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max; p.db_on = db_on; p.ph_off = ph_off;
+    if (fbm) { p.n_bands = n_bands; p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
     p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
     p.mc_wh = (!p.cosw || (hop & 1)) ? 1 : 0;
     p.mc_cl_in = (x_sc < x_sl) ? 1 : 0;

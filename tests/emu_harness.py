@@ -80,7 +80,7 @@ def emu_stft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt
 
 
 def emu_stft_mc(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, out_fmt,
-                amin=1e-5, ref=1.0, TF=2, n_warps=4, n_cta=3, db_on=0):
+                fb=None, amin=1e-5, ref=1.0, TF=2, n_warps=4, n_cta=3, db_on=0):
     """Multi-channel tile kernel (stft_mc_core.cuh); same conventions as emu_stft, TF = time frames per tile."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -94,23 +94,28 @@ def emu_stft_mc(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_
     Lp = L + pad_left
     T = -(-Lp // hop) if pad_end else max(0, 1 + (Lp - win_length) // hop)
     F = n_fft // 2 + 1
+    K = fb.shape[1] if mode in (MODE_FB, MODE_FB_DB) else F
     dt = np.complex64 if mode == MODE_COMPLEX else np.float32
     Co = 2 * C if mode == MODE_MAG_PHASE else C
     if out_fmt == 'channels_last':
-        out = np.full((B, T, F, Co), np.nan, dtype=dt)
-        osb, ost, osk, osc = T * F * Co, F * Co, Co, 1
+        out = np.full((B, T, K, Co), np.nan, dtype=dt)
+        osb, ost, osk, osc = T * K * Co, K * Co, Co, 1
     else:
-        out = np.full((B, Co, T, F), np.nan, dtype=dt)
-        osb, osc, ost, osk = Co * T * F, T * F, F, 1
+        out = np.full((B, Co, T, K), np.nan, dtype=dt)
+        osb, osc, ost, osk = Co * T * K, T * K, K, 1
     item_max = np.zeros(B, dtype=np.uint32)
     window = np.ascontiguousarray(window, dtype=np.float32)
+    fbp, nfreq, nb = None, 0, 0
+    if fb is not None:
+        fb = np.ascontiguousarray(fb, dtype=np.float32)
+        fbp, nfreq, nb = _fp(fb), fb.shape[0], fb.shape[1]
     db_mul = 10.0 * np.log10(2.0)
     db_sub = 10.0 * np.log10(max(amin, ref))
     LL = ctypes.c_longlong
     rc = lib.kb_emu_stft_mc(_fp(x), LL(sb), LL(sc), LL(sl), B, C, L, n_fft, win_length, hop, pad_left, T,
                             _fp(window), mode, _fp(out), LL(osb), LL(osc), LL(ost), LL(osk),
                             ctypes.c_float(amin), ctypes.c_float(db_mul), ctypes.c_float(db_sub), _fp(item_max),
-                            TF, n_warps, n_cta, db_on, LL(C * osc))
+                            TF, n_warps, n_cta, db_on, LL(C * osc), fbp, nfreq, nb)
     assert rc == 0, rc
     return out, item_max.view(np.float32)
 

@@ -148,3 +148,31 @@ def test_emu_mc_db_and_phase(fmt):
     d = np.abs(np.angle(np.exp(1j * (ph - np.angle(spec)))))
     assert d[ok].max() < 1e-4
     assert np.allclose(item_max, want_max, rtol=2e-6)
+
+
+@pytest.mark.parametrize('n_fft,hop,n_mels,sr,C,TF,nw', [(1024, 256, 128, 22050, 2, 8, 8), (1024, 256, 80, 16000, 3, 5, 8),
+                                                          (512, 128, 40, 16000, 4, 4, 4), (2048, 512, 96, 44100, 2, 2, 4),
+                                                          (2048, 1024, 64, 44100, 6, 1, 8), (256, 64, 20, 8000, 5, 6, 4)])
+@pytest.mark.parametrize('ifmt', ['channels_last', 'channels_first'])
+@pytest.mark.parametrize('ofmt', ['channels_last', 'channels_first'])
+def test_emu_mc_mel_and_db(n_fft, hop, n_mels, sr, C, TF, nw, ifmt, ofmt):
+    """Filterbank modes on all-channel tiles (kb_stft_mcfb_cta): partial rounds (TF*C < columns), interleaved
+    and planar copy-out, per-item maximum."""
+    rng = np.random.default_rng(n_mels + C)
+    B = 2
+    x = wave(rng, B, C, 6001, ifmt)
+    x[1] *= 1e-3
+    w = O.get_window(None, n_fft).astype(np.float32)
+    fb = O.filterbank_mel(sr, n_fft // 2 + 1, n_mels, 0.0, None, False, 'slaney')
+    kw = dict(n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels, pad_end=True, input_data_format=ifmt,
+              output_data_format=ofmt)
+    ref = O.melspectrogram_layer(x, return_decibel=False, **kw)
+    out, _ = E.emu_stft_mc(x, n_fft, n_fft, hop, w, False, True, E.MODE_FB, ifmt, ofmt, fb=fb, TF=TF, n_warps=nw)
+    assert out.shape == ref.shape
+    assert not np.isnan(out).any()
+    assert nerr(out, ref) < 2e-6
+    out, item_max = E.emu_stft_mc(x, n_fft, n_fft, hop, w, False, True, E.MODE_FB_DB, ifmt, ofmt, fb=fb, TF=TF,
+                                  n_warps=nw, n_cta=2)
+    ref_db = 10.0 * np.log10(np.maximum(ref, 1e-5))
+    assert np.abs(out - ref_db).max() < 1e-3
+    assert np.allclose(item_max, np.maximum(ref, 1e-5).reshape(B, -1).max(axis=1), rtol=3e-6)

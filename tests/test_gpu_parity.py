@@ -516,3 +516,29 @@ def test_cuda_graph_capture_matches_eager(K):
     assert np.array_equal(got_host, want.cpu().numpy())
     with pytest.raises(ValueError):
         cap(torch.zeros((2, 16000, 1), device='cuda'))
+
+
+def test_more_than_2_31_elements(K):
+    """Maximum sizes: a waveform tensor with > 2^31 elements (8.9 GB) -- every global offset must be
+    64-bit.  Items at both ends of the batch are checked against a small run of the same items."""
+    B, L = 8192, 270000
+    assert B * L > 2 ** 31
+    free, _ = torch.cuda.mem_get_info()
+    if free < 16 * 2 ** 30:
+        pytest.skip('needs 16 GB of free device memory')
+    layer = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=16000, n_mels=128, return_decibel=True,
+                                       input_data_format='channels_last', output_data_format='channels_last')
+    x = torch.empty((B, L, 1), device='cuda')
+    g = torch.Generator(device='cuda').manual_seed(3)
+    for i in range(0, B, 1024):          # fill in slabs (keeps the RNG call below 2^31 elements)
+        x[i:i + 1024].uniform_(-1, 1, generator=g)
+    x[B - 1] *= 1e-2
+    y = layer(x)
+    assert y.shape == (B, 1051, 128, 1)
+    for sl in (slice(0, 2), slice(B - 2, B), slice(B // 2, B // 2 + 1)):
+        small = layer(x[sl].clone())
+        assert torch.equal(y[sl], small)
+    assert torch.isfinite(y[::257]).all()
+    spec = K.STFT(n_fft=1024, hop_length=256)(x)           # complex output: 8192 * 1051 * 513 * 8 B = 35 GB
+    small = K.STFT(n_fft=1024, hop_length=256)(x[B - 1:].clone())
+    assert torch.equal(spec[B - 1:], small)
