@@ -729,7 +729,10 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands; p.n_fbw = fb->n_w;
         p.cw = fb->cw; p.cm = fb->cm; p.cg = fb->cg; p.n_chunks = fb->n_chunks;
     }
-    if (dbmode) { p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev; }
+    if (dbmode) {
+        p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev;
+        p.db_ftz = (db->amin >= 1.17549435e-38f) ? 1 : 0;
+    }
     if (mode == KAPRE_OUT_MAG_PHASE) { p.db_on = dbmode ? 1 : 0; p.ph_off = (long long)C * od->stride_c; }
     // interleaved (channels_last) tensors with several channels: tiles that hold all channels
     const bool strided_in = xd->stride_l != 1, strided_out = od->stride_f != 1;

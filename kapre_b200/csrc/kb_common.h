@@ -84,6 +84,7 @@ struct KbStftParams {
     int n_chunks;
     // decibel (modes *_DB): y = db_mul * log2(max(v, amin)) - db_sub; per-item max of max(v, amin)
     float amin, db_mul, db_sub;
+    int db_ftz;              // amin >= FLT_MIN: every clamped value is a normal float, log2 may flush denormals
     int db_on;               // KB_OUT_MAG_PHASE only: 1 = the magnitude half is decibel-scaled
     long long ph_off;        // KB_OUT_MAG_PHASE only: element offset from a magnitude to its phase
     unsigned int* item_max;  // B entries, uint view of non-negative floats, zero-initialised

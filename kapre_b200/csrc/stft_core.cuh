@@ -82,6 +82,7 @@ struct KbThreadRegs {
 #define KB_SYNC_CTA
 static inline float kb_sqrt(float v) { return std::sqrt(v); }
 static inline float kb_log2(float v) { return std::log2(v); }
+static inline float kb_lg2_ftz(float v) { return std::log2(v); }
 static inline float kb_atan2(float y, float x) { return std::atan2(y, x); }
 static inline float kb_ldg(const float* p) { return *p; }
 static inline void kb_atomic_max_u32(unsigned int* p, unsigned int v) { if (v > *p) *p = v; }
@@ -98,6 +99,7 @@ static inline void kb_bar_wait(KbBar*, unsigned) {}
 #define KB_SYNC_CTA __syncthreads()
 KB_D float kb_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 KB_D float kb_log2(float v) { return __log2f(v); }
+KB_D float kb_lg2_ftz(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 KB_D float kb_atan2(float y, float x) { return atan2f(y, x); }
 KB_D float kb_ldg(const float* p) { return __ldg(p); }
 KB_D void kb_atomic_max_u32(unsigned int* p, unsigned int v) { atomicMax(p, v); }
@@ -632,24 +634,53 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int M = p.n_bands;
                 const int sk = (int)p.o_sk;
                 const float amin = p.amin, dmul = p.db_mul, dsub = p.db_sub;
+                const bool ftz = p.db_ftz != 0;      // amin is a normal float: the bare MUFU.LG2 is exact enough
                 float rmax = R.runmax;
                 for (int colm = warp; colm < TF; colm += NW) {
                     const int t = t0 + colm;
                     if (t >= p.T) break;
-                    float* __restrict__ orow = o + (long long)t * p.o_st + (sk == 1 ? lane : lane * sk);
-                    const float* __restrict__ srow = out_s + colm * L.Mp + lane;
-                    const int step = 32 * sk;
-#pragma unroll 4
-                    for (int m = lane; m < M; m += 32) {
-                        float v = *srow;
-                        if (dbmode) {
-                            v = fmaxf(v, amin);
-                            rmax = fmaxf(rmax, v);
-                            v = dmul * kb_log2(v) - dsub;
+                    const float* __restrict__ srow = out_s + colm * L.Mp;
+                    if (sk == 1) {
+                        // contiguous rows: four values per lane and trip, immediate offsets
+                        float* __restrict__ orow = o + (long long)t * p.o_st;
+                        int m = lane;
+                        for (; m + 96 < M; m += 128) {
+                            float v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = srow[m + 32 * u];
+                            if (dbmode) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    v[u] = fmaxf(v[u], amin);
+                                    rmax = fmaxf(rmax, v[u]);
+                                    v[u] = dmul * (ftz ? kb_lg2_ftz(v[u]) : kb_log2(v[u])) - dsub;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) orow[m + 32 * u] = v[u];
                         }
-                        *orow = v;
-                        srow += 32;
-                        orow += step;
+                        for (; m < M; m += 32) {
+                            float v = srow[m];
+                            if (dbmode) {
+                                v = fmaxf(v, amin);
+                                rmax = fmaxf(rmax, v);
+                                v = dmul * (ftz ? kb_lg2_ftz(v) : kb_log2(v)) - dsub;
+                            }
+                            orow[m] = v;
+                        }
+                    } else {
+                        float* __restrict__ orow = o + (long long)t * p.o_st + lane * sk;
+                        const int step = 32 * sk;
+                        for (int m = lane; m < M; m += 32) {
+                            float v = srow[m];
+                            if (dbmode) {
+                                v = fmaxf(v, amin);
+                                rmax = fmaxf(rmax, v);
+                                v = dmul * (ftz ? kb_lg2_ftz(v) : kb_log2(v)) - dsub;
+                            }
+                            *orow = v;
+                            orow += step;
+                        }
                     }
                 }
                 R.runmax = rmax;

@@ -119,6 +119,7 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     p.x_lo = x; p.x_hi = x + x_numel; p.x_numel = x_numel; p.x_align = (unsigned)(((uintptr_t)x >> 2) & 3);
     p.bulk_ok = (bulk && x_sl == 1) ? 1 : 0; p.dbuf = dbuf;
     p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max; p.db_on = db_on; p.ph_off = ph_off;
+    p.db_ftz = (amin >= 1.17549435e-38f) ? 1 : 0;
     p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
     switch (Q) {
         case 4: run_stft<4>(p, n_cta); break;
@@ -160,6 +161,7 @@ int kb_emu_stft_mc(const float* x, long long x_sb, long long x_sc, long long x_s
     }
     p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
     p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max; p.db_on = db_on; p.ph_off = ph_off;
+    p.db_ftz = (amin >= 1.17549435e-38f) ? 1 : 0;
     if (fbm) { p.n_bands = n_bands; p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
     p.TF = TF; p.n_tiles_t = (T + TF - 1) / TF; p.n_warps = n_warps;
     p.mc_wh = (!p.cosw || (hop & 1)) ? 1 : 0;
