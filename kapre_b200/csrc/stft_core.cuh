@@ -278,6 +278,90 @@ KB_HD void kb_store_vec(float* dst, const float* src) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The register FFT of one frame column, shared by the single-channel kernel below and the
+// all-channel kernels of stft_mc_core.cuh.  A column is owned by the Q lanes (g, q = 0..Q-1) of a
+// warp; `region` is the warp's exchange buffer.  Between the three steps the warp synchronises.
+// ------------------------------------------------------------------------------------------
+#if defined(KB_HOST_EMU)
+#define KB_FN inline
+#else
+#define KB_FN __device__ __forceinline__
+#endif
+
+// Step 1: window the frame at `fr`, 32-point DFTs over z[q + Q j], twiddle, store transposed (32 x 33).
+//   wmode 2: cosine-sum window evaluated in registers (KbStftParams::cwq), samples read as aligned pairs
+//   wmode 1: window table, aligned pairs;  wmode 0: window table, scalar loads (odd sample offset)
+template <int Q>
+KB_FN void kb_col_window_dft32(KbThreadRegs& R, const float* fr, const float* __restrict__ wh_s,
+                               const kb_f4* __restrict__ cwq_s, float cw_a0, const cpx* __restrict__ twp_s,
+                               cpx* region, int g, int q, int wmode) {
+    if (wmode == 2) {
+        // 0.5 w[2(q + Q j) + {0,1}] = a0 - cc * cos(2 pi j / 32) + ss * sin(2 pi j / 32)
+        const kb_f4 cq = cwq_s[q];
+        const cpx cc = cmake(cq.x, cq.y), ss = cmake(cq.z, cq.w);
+        const cpx a0 = cmake(cw_a0, cw_a0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int n2 = 2 * (q + Q * j);
+            const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
+            const float cj = j <= 16 ? kb_cos32(j) : kb_cos32(32 - j);
+            const float sj = j <= 16 ? kb_sin32(j) : -kb_sin32(32 - j);
+            cpx wv = a0;
+            if (cj != 0.0f) wv = cfma_s(cc, -cj, wv);
+            if (sj != 0.0f) wv = cfma_s(ss, sj, wv);
+            R.v[j] = cmul_elem(xv, wv);
+        }
+    } else if (wmode == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int n2 = 2 * (q + Q * j);
+            const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
+            const cpx wv = *reinterpret_cast<const cpx*>(wh_s + n2);
+            R.v[j] = cmul_elem(xv, wv);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int n2 = 2 * (q + Q * j);
+            R.v[j] = cmake(fr[n2] * wh_s[n2], fr[n2 + 1] * wh_s[n2 + 1]);
+        }
+    }
+    kb_fft_dif<32>(R.v);
+    cpx* ex = region + (g * Q + q) * 33;
+    const cpx* tw = twp_s + q * 33;
+    ex[0] = R.v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) ex[k1] = cmul(R.v[kb_brev<32>(k1)], tw[k1]);
+}
+
+// Step 2: gather the lane's columns k1 = q + Q i of the transposed buffer.
+template <int Q>
+KB_FN void kb_col_gather(KbThreadRegs& R, const cpx* region, int g, int q) {
+    constexpr int FPW = 32 / Q;
+    const cpx* ex = region + (g * Q) * 33;
+#pragma unroll
+    for (int i = 0; i < FPW; ++i) {
+        const int k1 = q + Q * i;
+#pragma unroll
+        for (int q2 = 0; q2 < Q; ++q2) R.v[i * Q + q2] = ex[q2 * 33 + k1];
+    }
+}
+
+// Step 3: Q-point DFTs, natural-order store Z[k1 + 32 k2] at region + g * zstr (aliases the transpose buffer).
+template <int Q>
+KB_FN void kb_col_dftq_store(KbThreadRegs& R, cpx* region, int g, int q, int zstr) {
+    constexpr int FPW = 32 / Q;
+    cpx* zs = region + g * zstr;
+#pragma unroll
+    for (int i = 0; i < FPW; ++i) {
+        kb_fft_dif<Q>(R.v + i * Q);
+        const int k1 = q + Q * i;
+#pragma unroll
+        for (int k2 = 0; k2 < Q; ++k2) zs[k1 + 32 * k2] = R.v[i * Q + kb_brev<Q>(k2)];
+    }
+}
+
 // One CTA's share of the work: tiles cta, cta + n_cta, ...
 template <int Q, int MODE>
 #if defined(KB_HOST_EMU)
@@ -377,46 +461,9 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int warp = tid >> 5, lane = tid & 31;
                 const int g = lane / Q, q = lane % Q;
                 const int col = round * FR + warp * FPW + g;
-                if (col < TF) {
-                    const float* fr = smp_s + col * H;
-                    if (even_base && p.cosw) {
-                        // window in registers: 0.5 w[2(q + Q j) + {0,1}] = a0 - cc * cos(2 pi j / 32) + ss * sin(2 pi j / 32)
-                        const kb_f4 cq = cwq_s[q];
-                        const cpx cc = cmake(cq.x, cq.y), ss = cmake(cq.z, cq.w);
-                        const cpx a0 = cmake(p.cw_a0, p.cw_a0);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n2 = 2 * (q + Q * j);
-                            const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
-                            const float cj = j <= 16 ? kb_cos32(j) : kb_cos32(32 - j);
-                            const float sj = j <= 16 ? kb_sin32(j) : -kb_sin32(32 - j);
-                            cpx wv = a0;
-                            if (cj != 0.0f) wv = cfma_s(cc, -cj, wv);
-                            if (sj != 0.0f) wv = cfma_s(ss, sj, wv);
-                            R.v[j] = cmul_elem(xv, wv);
-                        }
-                    } else if (even_base) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n2 = 2 * (q + Q * j);
-                            const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
-                            const cpx wv = *reinterpret_cast<const cpx*>(wh_s + n2);
-                            R.v[j] = cmul_elem(xv, wv);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n2 = 2 * (q + Q * j);
-                            R.v[j] = cmake(fr[n2] * wh_s[n2], fr[n2 + 1] * wh_s[n2 + 1]);
-                        }
-                    }
-                    kb_fft_dif<32>(R.v);
-                    cpx* ex = ex_s + warp * EXS + (g * Q + q) * 33;
-                    const cpx* tw = twp_s + q * 33;
-                    ex[0] = R.v[0];
-#pragma unroll
-                    for (int k1 = 1; k1 < 32; ++k1) ex[k1] = cmul(R.v[kb_brev<32>(k1)], tw[k1]);
-                }
+                if (col < TF)
+                    kb_col_window_dft32<Q>(R, smp_s + col * H, wh_s, cwq_s, p.cw_a0, twp_s, ex_s + warp * EXS, g, q,
+                                           even_base ? (p.cosw ? 2 : 1) : 0);
             KB_PHASE_END
             if (round == n_rounds - 1 && !fbmode) {
                 // every warp has consumed the sample buffer: fetch the next tile behind phases 2-4
@@ -436,15 +483,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int warp = tid >> 5, lane = tid & 31;
                 const int g = lane / Q, q = lane % Q;
                 const int col = round * FR + warp * FPW + g;
-                if (col < TF) {
-                    const cpx* ex = ex_s + warp * EXS + (g * Q) * 33;
-#pragma unroll
-                    for (int i = 0; i < FPW; ++i) {
-                        const int k1 = q + Q * i;
-#pragma unroll
-                        for (int q2 = 0; q2 < Q; ++q2) R.v[i * Q + q2] = ex[q2 * 33 + k1];
-                    }
-                }
+                if (col < TF) kb_col_gather<Q>(R, ex_s + warp * EXS, g, q);
             KB_PHASE_END
             KB_SYNC_WARP;
             // ---- phase 3: Q-point DFTs, natural-order store (aliases the exchange buffer) ---
@@ -452,16 +491,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int warp = tid >> 5, lane = tid & 31;
                 const int g = lane / Q, q = lane % Q;
                 const int col = round * FR + warp * FPW + g;
-                if (col < TF) {
-                    cpx* zs = ex_s + warp * EXS + g * ZSTR;
-#pragma unroll
-                    for (int i = 0; i < FPW; ++i) {
-                        kb_fft_dif<Q>(R.v + i * Q);
-                        const int k1 = q + Q * i;
-#pragma unroll
-                        for (int k2 = 0; k2 < Q; ++k2) zs[k1 + 32 * k2] = R.v[i * Q + kb_brev<Q>(k2)];
-                    }
-                }
+                if (col < TF) kb_col_dftq_store<Q>(R, ex_s + warp * EXS, g, q, ZSTR);
             KB_PHASE_END
             KB_SYNC_WARP;
             // ---- phase 4: real-FFT pair post-processing + epilogue -------------------------

@@ -162,6 +162,8 @@ __device__ __forceinline__ void kb_mc_emit(const KbStftParams& p, bool dbany, vo
     }
 }
 
+// (The three FFT steps are written out in this body rather than calling the kb_col_* helpers of
+// stft_core.cuh: with the helpers ptxas schedules the Q = 32 instantiations 11 % slower -- measured on cfg3.)
 template <int Q, int MODE>
 #if defined(KB_HOST_EMU)
 inline void kb_stft_mc_cta(const KbStftParams& p, char* smem, int cta, int n_cta)
@@ -502,7 +504,7 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
     const int n_tiles = p.B * p.n_tiles_t;
     const int span = L.span, spanp = L.spanp;
     const bool even_base = (H & 1) == 0;
-    const bool use_cosw = even_base && p.cosw;
+    const int wmode = even_base ? (p.cosw ? 2 : 1) : 0;   // see kb_col_window_dft32
 
 #if defined(KB_HOST_EMU)
     std::vector<KbThreadRegs> kb_regs(kb_nt);
@@ -549,43 +551,8 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
             const int col = warp * FPW + g;
             if (col < NCOL) {
                 const int fl = kb_fdiv(col, C, p.mc_magic_c), ch = col - fl * C;
-                const float* fr = smp + ch * spanp + fl * H;
-                if (use_cosw) {
-                    const kb_f4 cq = cwq_s[q];
-                    const cpx cc = cmake(cq.x, cq.y), ss = cmake(cq.z, cq.w);
-                    const cpx a0 = cmake(p.cw_a0, p.cw_a0);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n2 = 2 * (q + Q * j);
-                        const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
-                        const float cj = j <= 16 ? kb_cos32(j) : kb_cos32(32 - j);
-                        const float sj = j <= 16 ? kb_sin32(j) : -kb_sin32(32 - j);
-                        cpx wv = a0;
-                        if (cj != 0.0f) wv = cfma_s(cc, -cj, wv);
-                        if (sj != 0.0f) wv = cfma_s(ss, sj, wv);
-                        R.v[j] = cmul_elem(xv, wv);
-                    }
-                } else if (even_base) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n2 = 2 * (q + Q * j);
-                        const cpx xv = *reinterpret_cast<const cpx*>(fr + n2);
-                        const cpx wv = *reinterpret_cast<const cpx*>(wh_s + n2);
-                        R.v[j] = cmul_elem(xv, wv);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n2 = 2 * (q + Q * j);
-                        R.v[j] = cmake(fr[n2] * wh_s[n2], fr[n2 + 1] * wh_s[n2 + 1]);
-                    }
-                }
-                kb_fft_dif<32>(R.v);
-                cpx* ex = ex_s + warp * EXS + (g * Q + q) * 33;
-                const cpx* tw = twp_s + q * 33;
-                ex[0] = R.v[0];
-#pragma unroll
-                for (int k1 = 1; k1 < 32; ++k1) ex[k1] = cmul(R.v[kb_brev<32>(k1)], tw[k1]);
+                kb_col_window_dft32<Q>(R, smp + ch * spanp + fl * H, wh_s, cwq_s, p.cw_a0, twp_s, ex_s + warp * EXS, g, q,
+                                       wmode);
             }
         KB_PHASE_END
         KB_SYNC_WARP;
@@ -593,31 +560,14 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
         KB_PHASE_BEGIN
             const int warp = tid >> 5, lane = tid & 31;
             const int g = lane / Q, q = lane % Q;
-            if (warp * FPW + g < NCOL) {
-                const cpx* ex = ex_s + warp * EXS + (g * Q) * 33;
-#pragma unroll
-                for (int i = 0; i < FPW; ++i) {
-                    const int k1 = q + Q * i;
-#pragma unroll
-                    for (int q2 = 0; q2 < Q; ++q2) R.v[i * Q + q2] = ex[q2 * 33 + k1];
-                }
-            }
+            if (warp * FPW + g < NCOL) kb_col_gather<Q>(R, ex_s + warp * EXS, g, q);
         KB_PHASE_END
         KB_SYNC_WARP;
         // ---- phase 3: Q-point DFTs, natural-order store ---------------------------------------
         KB_PHASE_BEGIN
             const int warp = tid >> 5, lane = tid & 31;
             const int g = lane / Q, q = lane % Q;
-            if (warp * FPW + g < NCOL) {
-                cpx* zs = ex_s + warp * EXS + g * ZSTR;
-#pragma unroll
-                for (int i = 0; i < FPW; ++i) {
-                    kb_fft_dif<Q>(R.v + i * Q);
-                    const int k1 = q + Q * i;
-#pragma unroll
-                    for (int k2 = 0; k2 < Q; ++k2) zs[k1 + 32 * k2] = R.v[i * Q + kb_brev<Q>(k2)];
-                }
-            }
+            if (warp * FPW + g < NCOL) kb_col_dftq_store<Q>(R, ex_s + warp * EXS, g, q, ZSTR);
         KB_PHASE_END
         KB_SYNC_WARP;
         // ---- phase 4: pair step, magnitudes parked in registers (R.v is dead) -------------------
