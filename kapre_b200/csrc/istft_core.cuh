@@ -105,19 +105,36 @@ __device__ __forceinline__ void kb_istft_cta(const KbIstftParams& p, char* smem,
                 KB_PHASE_BEGIN
                     (void)R;
                     const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll 1
+                    // all of the round's global loads are issued before the first use (FPW frames x Q/2 bin pairs)
+                    float2 xa[FPW][Q / 2], xb[FPW][Q / 2], xm[FPW];
+                    bool live[FPW];
+#pragma unroll
                     for (int gg = 0; gg < FPW; ++gg) {
                         const int idx = round * FR + warp * FPW + gg;
                         const int fi = cl + R_ * idx;
                         const int t = tf0 + fi;
-                        if (fi >= TFc || t < 0 || t >= p.T) continue;
-                        const float2* Xf = Xsig + (long long)t * p.x_st;
+                        live[gg] = !(fi >= TFc || t < 0 || t >= p.T);
+                        xm[gg] = make_float2(0.0f, 0.0f);
+                        if (live[gg]) {
+                            const float2* Xf = Xsig + (long long)t * p.x_st;
+#pragma unroll
+                            for (int i = 0; i < Q / 2; ++i) {
+                                const int k = lane + 32 * i;
+                                xa[gg][i] = Xf[(long long)k * p.x_sk];
+                                xb[gg][i] = Xf[(long long)(P - k) * p.x_sk];
+                            }
+                            if (lane == 0) xm[gg] = Xf[(long long)(P / 2) * p.x_sk];
+                        }
+                    }
+#pragma unroll
+                    for (int gg = 0; gg < FPW; ++gg) {
+                        if (!live[gg]) continue;
                         cpx* zf = ex_s + warp * EXW + gg * ZSTR;
 #pragma unroll
                         for (int i = 0; i < Q / 2; ++i) {
                             const int k = lane + 32 * i;
-                            float2 a = Xf[(long long)k * p.x_sk];
-                            float2 bq = Xf[(long long)(P - k) * p.x_sk];
+                            float2 a = xa[gg][i];
+                            float2 bq = xb[gg][i];
                             if (k == 0) { a.y = 0.0f; bq.y = 0.0f; }  // C2R ignores Im of DC / Nyquist
                             const cpx W = twn_s[k];
                             const float Er = a.x + bq.x, Ei = a.y - bq.y;
@@ -127,10 +144,7 @@ __device__ __forceinline__ void kb_istft_cta(const KbIstftParams& p, char* smem,
                             zf[k] = cmake(Er - Oi, -(Ei + Or));
                             if (k != 0) zf[P - k] = cmake(Er + Oi, Ei - Or);
                         }
-                        if (lane == 0) {
-                            const float2 a = Xf[(long long)(P / 2) * p.x_sk];
-                            zf[P / 2] = cmake(2.0f * a.x, 2.0f * a.y);
-                        }
+                        if (lane == 0) zf[P / 2] = cmake(2.0f * xm[gg].x, 2.0f * xm[gg].y);
                     }
                 KB_PHASE_END
                 KB_SYNC_WARP;
@@ -181,6 +195,7 @@ __device__ __forceinline__ void kb_istft_cta(const KbIstftParams& p, char* smem,
                             for (int q2 = 0; q2 < Q; ++q2) R.v[i * Q + q2] = ex[q2 * 33 + k1];
                         }
                         float* of = ola_s + fi * H;
+                        const bool pair_ok = ((fi * H) & 1) == 0;
 #pragma unroll
                         for (int i = 0; i < FPW; ++i) {
                             kb_fft_dif<Q>(R.v + i * Q);
@@ -189,8 +204,14 @@ __device__ __forceinline__ void kb_istft_cta(const KbIstftParams& p, char* smem,
                             for (int k2 = 0; k2 < Q; ++k2) {
                                 const int m2 = 2 * (k1 + 32 * k2);
                                 const cpx r = R.v[i * Q + kb_brev<Q>(k2)];
-                                if (m2 < win) of[m2] += r.re * dual_s[m2];
-                                if (m2 + 1 < win) of[m2 + 1] += r.im * dual_s[m2 + 1];
+                                if (pair_ok && m2 + 1 < win) {      // aligned sample pair: one 8-byte read-modify-write
+                                    cpx* o2 = reinterpret_cast<cpx*>(of + m2);
+                                    const cpx d2 = *reinterpret_cast<const cpx*>(dual_s + m2);
+                                    *o2 = cadd(*o2, cmul_elem(r, d2));
+                                } else {
+                                    if (m2 < win) of[m2] += r.re * dual_s[m2];
+                                    if (m2 + 1 < win) of[m2 + 1] += r.im * dual_s[m2 + 1];
+                                }
                             }
                         }
                     }

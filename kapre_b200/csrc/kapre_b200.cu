@@ -88,8 +88,11 @@ __global__ void __launch_bounds__(512, 1) kb_stft_mc_kernel(const __grid_constan
     kb_stft_mc_cta<Q, MODE>(p, kb_smem, blockIdx.x, gridDim.x);
 }
 
+// 4 warps per CTA (one FFT round per overlap class), two or three CTAs per SM: the register file is not the
+// limit here, so the kernel may use up to 168 registers and keeps the round's global loads in flight.
+#define KB_ISTFT_MAX_WARPS 4
 template <int Q>
-__global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_istft_kernel(const __grid_constant__ KbIstftParams p) {
+__global__ void __launch_bounds__(KB_ISTFT_MAX_WARPS * 32, 3) kb_istft_kernel(const __grid_constant__ KbIstftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
     kb_istft_cta<Q>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
@@ -901,7 +904,8 @@ int kapre_istft_inverse(const kapre_istft_plan* plan, const void* stft_dev, int 
     const int Q = plan->Q, FPW = 32 / Q;
     const int R = (plan->win + plan->hop - 1) / plan->hop;
     // one FFT round per overlap class: TFc = R * NW * FPW frames per tile
-    int NW = kb_env_int("KAPRE_B200_INW", 4), TFc = 0, smem = 0, bps = 0;
+    int NW = kb_env_int("KAPRE_B200_INW", KB_ISTFT_MAX_WARPS), TFc = 0, smem = 0, bps = 0;
+    if (NW > KB_ISTFT_MAX_WARPS || NW < 1) NW = KB_ISTFT_MAX_WARPS;
     for (;; NW >>= 1) {
         if (NW < 1) return kb_fail(KAPRE_E_UNSUPPORTED, "inverse STFT tile does not fit shared memory (n_fft=%d hop=%d)", plan->n_fft, plan->hop);
         TFc = R * NW * FPW;
@@ -911,7 +915,7 @@ int kapre_istft_inverse(const kapre_istft_plan* plan, const void* stft_dev, int 
         if (smem <= plan->dev.smem_optin) break;
     }
     bps = (228 * 1024) / (smem + 1024);
-    if (bps > 64 / NW) bps = 64 / NW;
+    if (bps > 3) bps = 3;              // __launch_bounds__(128, 3): 168 registers per thread
     if (bps < 1) bps = 1;
     KbIstftParams p{};
     p.X = (const float2*)stft_dev; p.x_sb = sd->stride_b; p.x_sc = sd->stride_c; p.x_st = sd->stride_t; p.x_sk = sd->stride_f;
