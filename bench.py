@@ -194,6 +194,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     _native.lib()
     layer = K.get_melspectrogram_layer(n_fft=CFG['n_fft'], hop_length=CFG['hop'], sample_rate=CFG['sample_rate'],
