@@ -326,7 +326,7 @@ def main():
         except Exception:
             pass
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is an N=1 measurement (rank 0 has the box to itself)
         cpu, _ = run_cpu(steps=40, warmup=1, budget_s=12.0)
     line = {
         'metric': 'mel_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
