@@ -2,6 +2,8 @@
 committed golden fixtures.  Tolerances are written next to each assertion; the reference's own
 tolerances (tests/test_time_frequency.py:65-69,120,256,265-267,486; tests/test_backend.py:12,40)
 are asserted as well where a reference test is mirrored."""
+import os
+
 import numpy as np
 import pytest
 
@@ -542,3 +544,36 @@ def test_more_than_2_31_elements(K):
     spec = K.STFT(n_fft=1024, hop_length=256)(x)           # complex output: 8192 * 1051 * 513 * 8 B = 35 GB
     small = K.STFT(n_fft=1024, hop_length=256)(x[B - 1:].clone())
     assert torch.equal(spec[B - 1:], small)
+
+
+def test_c_client_matches_oracle(tmp_path):
+    """The C ABI driven from plain C (tests/abi_c/abi_example.c: cudaMalloc / cudaMemcpy + libkapre_b200.so, no
+    Python or torch in that process) reproduces the oracle's log-mel spectrogram."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_api import _build_c_client
+    exe = _build_c_client(str(tmp_path / 'abi_example'))
+    rng = np.random.default_rng(21)
+    B, L, n_fft, hop, n_mels, sr = 3, 20000, 1024, 256, 128, 22050
+    x = rng.uniform(-1, 1, size=(B, L)).astype(np.float32)
+    x[1] *= 1e-2
+    win = O.get_window(None, n_fft).astype(np.float32)
+    fb = O.filterbank_mel(sr, n_fft // 2 + 1, n_mels, 0.0, None, False, 'slaney').astype(np.float32)
+    x.tofile(tmp_path / 'wave.f32')
+    win.tofile(tmp_path / 'window.f32')
+    np.ascontiguousarray(fb).tofile(tmp_path / 'fb.f32')
+    out = subprocess.run([exe, str(tmp_path / 'wave.f32'), str(B), str(L), str(tmp_path / 'window.f32'), str(n_fft),
+                          str(hop), str(tmp_path / 'fb.f32'), str(n_mels), str(tmp_path / 'out.f32')],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    T = 1 + (L - n_fft) // hop
+    got = np.fromfile(tmp_path / 'out.f32', dtype=np.float32).reshape(B, T, n_mels)
+    ref = O.melspectrogram_layer(x[:, :, None], n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels,
+                                 return_decibel=True, input_data_format='channels_last',
+                                 output_data_format='channels_last')[..., 0]
+    assert np.abs(got - ref).max() < 1e-3
+    assert 'launches=4' in out.stdout          # 2 calls x (fused kernel + clamp)

@@ -232,3 +232,26 @@ def test_predict_result_buffers_are_recycled_only_when_released(monkeypatch):
     n4 = get()
     assert n4.ctypes.data == p1                           # released -> recycled, no new allocation
     assert len(seq._result_pool) == 3
+
+
+def _build_c_client(out_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, 'kapre_b200', '_lib')
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    cmd = ['gcc', '-std=c11', '-O1', '-Wall', '-Werror', '-I' + os.path.join(root, 'include'),
+           '-I' + os.path.join(cuda, 'include'), os.path.join(root, 'tests', 'abi_c', 'abi_example.c'), '-o', out_path,
+           '-L' + lib_dir, '-lkapre_b200', '-L' + os.path.join(cuda, 'lib64'), '-lcudart',
+           '-Wl,-rpath,' + lib_dir, '-Wl,-rpath,' + os.path.join(cuda, 'lib64')]
+    subprocess.check_call(cmd)
+    return out_path
+
+
+def test_header_is_plain_c_and_c_client_links(tmp_path):
+    """include/kapre_b200.h must be usable from C (no C++ / torch / CUDA types): the plain-C client of
+    tests/abi_c compiles with gcc -std=c11 -Wall -Werror and links against libkapre_b200.so."""
+    import shutil
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    exe = _build_c_client(str(tmp_path / 'abi_example'))
+    assert os.path.exists(exe)
