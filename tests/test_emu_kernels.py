@@ -105,7 +105,8 @@ def test_emu_istft(n_fft, hop, win, TFc, nw, ifmt, ofmt):
 @pytest.mark.parametrize('n_fft,hop,win,C,TF,nw', [(2048, 1024, 2048, 6, 1, 6), (2048, 1024, 2048, 6, 2, 4),
                                                   (1024, 256, 1024, 2, 8, 8), (512, 128, 400, 3, 3, 2),
                                                   (256, 64, 256, 5, 4, 3), (1024, 255, 1024, 2, 2, 1),
-                                                  (512, 256, 512, 4, 5, 4)])
+                                                  (512, 256, 512, 4, 5, 4), (256, 64, 256, 12, 2, 4),
+                                                  (512, 128, 512, 31, 1, 2)])
 @pytest.mark.parametrize('ifmt', ['channels_last', 'channels_first'])
 @pytest.mark.parametrize('ofmt', ['channels_last', 'channels_first'])
 def test_emu_mc_complex_and_mag(n_fft, hop, win, C, TF, nw, ifmt, ofmt):
