@@ -133,6 +133,19 @@ def main():
         model = getattr(KC, fn)(**kw)
         record('composed_%d' % i, fn, kw, in_key, model(x64(in_key)))
 
+    # ---- get_stft_mag_phase: composed.py:420-511 (keras functional API: Input -> STFT -> Magnitude || Phase -> Concatenate)
+    for i, (kw, in_key) in enumerate([
+            (dict(n_fft=512, hop_length=128, return_decibel=True), 'speech_cl'),
+            (dict(n_fft=1024, hop_length=256, return_decibel=False, pad_end=True), 'noise_cl'),
+            (dict(n_fft=512, hop_length=256, return_decibel=True, db_dynamic_range=40.0,
+                  input_data_format='channels_first', output_data_format='channels_first'), 'noise_cf')]):
+        kw = dict(kw)
+        kw.setdefault('input_data_format', 'channels_last')
+        kw.setdefault('output_data_format', 'channels_last')
+        shape = inputs[in_key].shape[1:]
+        model = KC.get_stft_mag_phase(input_shape=shape, **kw)
+        record('mag_phase_%d' % i, 'get_stft_mag_phase', dict(kw, input_shape=list(shape)), in_key, model(x64(in_key)))
+
     # ---- InverseSTFT: time_frequency.py:207-333, composed.py:417-433 -----------------------------
     for i, (kw, in_key) in enumerate([(dict(n_fft=512, hop_length=128), 'noise_cl'),
                                       (dict(n_fft=1024, win_length=1024, hop_length=256,

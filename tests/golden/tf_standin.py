@@ -189,6 +189,25 @@ def mfccs_from_log_mel_spectrograms(log_mel_spectrograms, name=None):
 
 
 # ------------------------------------------------------------------------------------ keras
+class _Sym:
+    """Node of a functional-API graph (keras.Input / layer(sym)): evaluated lazily by Model.__call__."""
+
+    def __init__(self, layer=None, parents=()):
+        self.layer, self.parents = layer, tuple(parents)
+
+    def evaluate(self, feed):
+        if self in feed:
+            return feed[self]
+        args = [p.evaluate(feed) for p in self.parents]
+        val = self.layer.call(args if getattr(self.layer, '_takes_list', False) else args[0])
+        feed[self] = val
+        return val
+
+
+def Input(shape=None, **kwargs):
+    return _Sym()
+
+
 class Layer:
     _counters = {}
 
@@ -202,10 +221,36 @@ class Layer:
         self.trainable = trainable
 
     def __call__(self, x, *a, **k):
+        if isinstance(x, _Sym):
+            return _Sym(self, [x])
+        if isinstance(x, (list, tuple)) and x and all(isinstance(v, _Sym) for v in x):
+            return _Sym(self, list(x))
         return self.call(x, *a, **k)
 
     def get_config(self):
         return {'name': self.name, 'trainable': self.trainable}
+
+
+class Concatenate(Layer):
+    _takes_list = True
+
+    def __init__(self, axis=-1, **kwargs):
+        super().__init__(**kwargs)
+        self.axis = axis
+
+    def call(self, xs):
+        return np.concatenate(list(xs), axis=self.axis)
+
+
+class Model(Layer):
+    """keras.Model(inputs=sym, outputs=sym): runs the recorded layer graph eagerly."""
+
+    def __init__(self, inputs=None, outputs=None, name=None):
+        super().__init__(name=name)
+        self.inputs, self.outputs = inputs, outputs
+
+    def call(self, x):
+        return self.outputs.evaluate({self.inputs: x})
 
 
 class Sequential(Layer):
@@ -376,7 +421,9 @@ def install():
     keras.utils = utils
     utils.register_keras_serializable = register_keras_serializable
     keras.Sequential = Sequential
-    keras.Model = Sequential
+    keras.Model = Model
+    keras.Input = Input
+    layers.Concatenate = Concatenate
     sys.modules['keras'] = keras   # "from tensorflow import keras" / "import keras.config" fallbacks
 
     librosa = _mod('librosa')

@@ -70,6 +70,9 @@ def _oracle(case):
         fb = O.filterbank_log(sr, n_fft // 2 + 1, kw['log_n_bins'], 12, None, 0.125)
         y = O.apply_filterbank(s, fb, kw['output_data_format'])
         return O.magnitude_to_decibel(y) if kw['return_decibel'] else y
+    if kind == 'get_stft_mag_phase':
+        kw.pop('input_shape')
+        return O.stft_mag_phase_layer(x, **kw)
     if kind == 'InverseSTFT':
         return O.istft_layer(x, **kw)
     if kind == 'get_perfectly_reconstructing_stft_istft':
@@ -140,6 +143,9 @@ def _cuda(case, K):
         return np.asarray(K.backend.filterbank_log(**kw))
     if kind in ('get_stft_magnitude_layer', 'get_melspectrogram_layer', 'get_log_frequency_spectrogram_layer'):
         return getattr(K, kind)(**kw)(x)
+    if kind == 'get_stft_mag_phase':
+        kw['input_shape'] = tuple(kw['input_shape'])
+        return K.get_stft_mag_phase(**kw)(x)
     if kind == 'get_perfectly_reconstructing_stft_istft':
         stft, istft = K.get_perfectly_reconstructing_stft_istft(**kw)
         return istft(stft(x))
@@ -173,9 +179,24 @@ def test_cuda_reproduces_reference_run(key):
         d = np.abs(np.angle(np.exp(1j * (got.astype(np.float64) - want))))
         assert d[ok].max() < 2e-3
         return
+    kind, kw = case['kind'], case['kwargs']
+    if kind == 'get_stft_mag_phase':
+        # magnitude half: linear / decibel tolerance; phase half: angular distance where the bin is not at the
+        # fp32 round-off floor (the angle of a numerically-zero bin is not determined)
+        ax = 1 if kw['output_data_format'] == 'channels_first' else 3
+        gm, gp = np.split(got.astype(np.float64), 2, axis=ax)
+        wm, wp = np.split(want.astype(np.float64), 2, axis=ax)
+        lin_w = 10.0 ** (wm / 10.0) if kw['return_decibel'] else wm
+        lin_g = 10.0 ** (gm / 10.0) if kw['return_decibel'] else gm
+        assert np.abs(lin_g - lin_w).max() <= 3e-6 * lin_w.max() + 1e-7
+        if kw['return_decibel']:
+            strong = lin_w > 1e-3 * lin_w.max()
+            assert np.abs(gm - wm)[strong].max() < 2e-3
+        strong = lin_w > 1e-3 * lin_w.max()
+        assert np.abs(np.angle(np.exp(1j * (gp - wp))))[strong].max() < 2e-3
+        return
     tol = _gpu_tolerance(case, want)
     diff = np.abs(got.astype(want.dtype) - want)
-    kind, kw = case['kind'], case['kwargs']
     if kind in ('MagnitudeToDecibel', 'backend.magnitude_to_decibel') or kw.get('return_decibel'):
         # decibel outputs: values whose LINEAR magnitude sits at the fp32 round-off floor of the FFT
         # (5e-7 of the item's peak, e.g. the far skirts of a pure tone around amin) are compared on
