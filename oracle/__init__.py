@@ -10,7 +10,7 @@ neither is installed (no network) and the repository stores no golden output vec
 compare against librosa evaluated at test time).  ``tests/golden/make_golden_ref.py`` therefore
 imports the UNMODIFIED sources under /root/reference/kapre over ``tests/golden/tf_standin.py`` -- a
 NumPy stand-in for the TensorFlow / Keras / librosa entry points they call -- and records what the
-reference's layers and composed models return for 52 cases (``tests/golden/kapre_ref_cases.*``);
+reference's layers and composed models return for 55 cases (``tests/golden/kapre_ref_cases.*``);
 ``tests/test_ref_golden.py`` holds the oracle (CPU tier) and the CUDA path (GPU tier) to them.
 
 * Pinned by the reference's own code: everything kapre itself does -- data-format transposes,
