@@ -75,6 +75,14 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel(const __g
     kb_stft_cta<Q, MODE>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
+// 16-warp CTAs, one per SM: n_fft = 2048 in the filterbank modes, where an 8-warp CTA already needs more than
+// half of the SM's shared memory (8.4 KB of exchange buffer per warp), so two CTAs never fit
+template <int Q, int MODE>
+__global__ void __launch_bounds__(512, 1) kb_stft_kernel_w16(const __grid_constant__ KbStftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_stft_cta<Q, MODE>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
 template <int Q, int MODE>
 __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_mcfb_kernel(const __grid_constant__ KbStftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
@@ -324,7 +332,7 @@ struct FwdCfg { int TF, NW, smem, bps; };
 // most, then larger tiles (less re-staging of the hop overlap).  Filterbank modes keep the
 // tile's magnitudes in the warps' exchange regions, which needs TF == frames per round.
 static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int mode, int n_bands, int n_chunks,
-                            FwdCfg* out) {
+                            int with_wh, FwdCfg* out) {
     const int FPW = 32 / Q;
     const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     const int force_tf = kb_env_int("KAPRE_B200_TF", 0);
@@ -333,23 +341,22 @@ static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int m
     bool found = false;
     FwdCfg best{};
     long best_score = -1;
-    const int nws[3] = {2, 4, 8};
-    for (int a = 0; a < 3; ++a) {
+    const int nws[4] = {2, 4, 8, 16};
+    for (int a = 0; a < 4; ++a) {
         const int NW = nws[a];
         if (force_nw && NW != force_nw) continue;
+        if (NW == 16 && !(Q == 32 && fb)) continue;      // only kb_stft_kernel_w16's instantiations
         const int FR = NW * FPW;
         if (FR > 32) continue;
         for (int TF = 32; TF >= 1; TF >>= 1) {
             if (fb ? (TF != FR) : (TF % FR != 0)) continue;
             if (!fb && force_tf && TF != force_tf) continue;
-            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands, n_chunks);
+            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands, n_chunks, with_wh);
             if (L.total > dev.smem_optin) continue;
             int bps = sm_smem / (L.total + 1024);
-            if (bps > 64 / NW) bps = 64 / NW;
-            if (bps > 32) bps = 32;
+            if (bps > 16 / NW) bps = 16 / NW;                 // 128 registers per thread: 16 warps per SM
             if (bps < 1) continue;
-            int warps = bps * NW;
-            if (warps > 16) warps = 16;
+            const int warps = bps * NW;
             const long score = (long)warps * 1000 + TF * 10 + NW;
             if (score > best_score) {
                 best_score = score;
@@ -371,6 +378,19 @@ static int kb_set_smem(K kernel, int smem) {
 
 template <int Q, int MODE>
 static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
+    if (p.n_warps > KB_MAX_WARPS) {
+        if constexpr (Q == 32 && (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB)) {
+            int rc = kb_set_smem(kb_stft_kernel_w16<Q, MODE>, smem);
+            if (rc) return rc;
+            KbProfScope prof(st);
+            kb_stft_kernel_w16<Q, MODE><<<grid, p.n_warps * 32, smem, st>>>(p);
+            KB_CUDA(cudaGetLastError());
+            g_launches++;
+            return 0;
+        } else {
+            return kb_fail(KAPRE_E_UNSUPPORTED, "no 16-warp instantiation for Q=%d mode=%d", Q, MODE);
+        }
+    }
     int rc = kb_set_smem(kb_stft_kernel<Q, MODE>, smem);
     if (rc) return rc;
     KbProfScope prof(st);
@@ -716,7 +736,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
                       kb_env_int("KAPRE_B200_NOBULK", 0) == 0;
     FwdCfg cfg;
     if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0,
-                         fbmode ? fb->n_chunks : 0, &cfg))
+                         fbmode ? fb->n_chunks : 0, 1, &cfg))
         return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
                        plan->n_fft, plan->hop, fbmode ? fb->n_bands : 0);
     KbStftParams p{};

@@ -177,3 +177,22 @@ def test_emu_mc_mel_and_db(n_fft, hop, n_mels, sr, C, TF, nw, ifmt, ofmt):
     ref_db = 10.0 * np.log10(np.maximum(ref, 1e-5))
     assert np.abs(out - ref_db).max() < 1e-3
     assert np.allclose(item_max, np.maximum(ref, 1e-5).reshape(B, -1).max(axis=1), rtol=3e-6)
+
+
+def test_emu_sixteen_warp_cta_n2048_mel():
+    """n_fft = 2048 filterbank modes run 16-warp CTAs (kb_stft_kernel_w16): TF = 16 frames per tile."""
+    rng = np.random.default_rng(16)
+    x = wave(rng, 2, 1, 30000, 'channels_last')
+    x[1] *= 1e-2
+    w = O.get_window(None, 2048).astype(np.float32)
+    fb = O.filterbank_mel(44100, 1025, 128, 0.0, None, False, 'slaney')
+    kw = dict(n_fft=2048, hop_length=512, sample_rate=44100, n_mels=128, input_data_format='channels_last',
+              output_data_format='channels_last')
+    ref = O.melspectrogram_layer(x, return_decibel=False, **kw)
+    out, _ = E.emu_stft(x, 2048, 2048, 512, w, False, False, E.MODE_FB, 'channels_last', 'channels_last', fb=fb,
+                        TF=16, n_warps=16, n_cta=2)
+    assert nerr(out, ref) < 2e-6
+    out, item_max = E.emu_stft(x, 2048, 2048, 512, w, False, False, E.MODE_FB_DB, 'channels_last', 'channels_last',
+                               fb=fb, TF=16, n_warps=16, n_cta=3)
+    assert np.abs(out - 10.0 * np.log10(np.maximum(ref, 1e-5))).max() < 1e-3
+    assert np.allclose(item_max, np.maximum(ref, 1e-5).reshape(2, -1).max(axis=1), rtol=3e-6)
