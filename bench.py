@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# NCCL's debug / banner output must not end up on stdout (one JSON line goes there)
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -195,9 +198,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) with
+        # C stdio to fd 1, so fd 1 points at stderr while the communicator is created
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()                      # creates the communicator (lazy in torch)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     _native.lib()
     layer = K.get_melspectrogram_layer(n_fft=CFG['n_fft'], hop_length=CFG['hop'], sample_rate=CFG['sample_rate'],
                                        n_mels=CFG['n_mels'], return_decibel=True, input_data_format='channels_last',
