@@ -332,7 +332,7 @@ struct FwdCfg { int TF, NW, smem, bps; };
 // most, then larger tiles (less re-staging of the hop overlap).  Filterbank modes keep the
 // tile's magnitudes in the warps' exchange regions, which needs TF == frames per round.
 static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int mode, int n_bands, int n_chunks,
-                            int with_wh, FwdCfg* out) {
+                            FwdCfg* out) {
     const int FPW = 32 / Q;
     const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     const int force_tf = kb_env_int("KAPRE_B200_TF", 0);
@@ -351,7 +351,7 @@ static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int m
         for (int TF = 32; TF >= 1; TF >>= 1) {
             if (fb ? (TF != FR) : (TF % FR != 0)) continue;
             if (!fb && force_tf && TF != force_tf) continue;
-            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands, n_chunks, with_wh);
+            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands, n_chunks);
             if (L.total > dev.smem_optin) continue;
             int bps = sm_smem / (L.total + 1024);
             if (bps > 16 / NW) bps = 16 / NW;                 // 128 registers per thread: 16 warps per SM
@@ -736,7 +736,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
                       kb_env_int("KAPRE_B200_NOBULK", 0) == 0;
     FwdCfg cfg;
     if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0,
-                         fbmode ? fb->n_chunks : 0, 1, &cfg))
+                         fbmode ? fb->n_chunks : 0, &cfg))
         return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
                        plan->n_fft, plan->hop, fbmode ? fb->n_bands : 0);
     KbStftParams p{};
@@ -805,12 +805,6 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
         tiles = (long long)B * C * p.n_tiles_t;
         if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
-        const int force_bps = kb_env_int("KAPRE_B200_BPS", 0);   // experiment: CTAs per SM (occupancy study)
-        if (force_bps > 0 && force_bps < cfg.bps) {
-            cfg.bps = force_bps;
-            const int want = (228 * 1024) / force_bps - 2048;   // pad the request so that no more CTAs fit
-            if (want > cfg.smem && want <= plan->dev.smem_optin) cfg.smem = want;
-        }
         const long long gmax = (long long)plan->dev.sm_count * cfg.bps;
         grid = (int)(tiles < gmax ? tiles : gmax);
         switch (plan->Q) {

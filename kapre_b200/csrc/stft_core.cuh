@@ -44,12 +44,12 @@ KB_HD int kb_exw(int Q) {
 
 // Shared-memory carve-up; used by the host launcher (size) and by the kernel (offsets).
 KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_warps, int mode,
-                                     int n_bands, int n_chunks, int with_wh) {
+                                     int n_bands, int n_chunks) {
     KbStftSmem s;
     const int P = 32 * Q;
     const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     int off = 0;
-    s.wh = off;  if (with_wh) off += kb_align16(n_fft * 4);   // not needed when the window is evaluated in registers
+    s.wh = off;  off += kb_align16(n_fft * 4);
     s.twp = off; off += kb_align16(Q * 33 * 8);
     s.twn = off; off += kb_align16((P / 2) * 8);
     s.cwq = off; off += Q * 16;
@@ -380,7 +380,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     const int kb_nt = NW * 32;
     (void)kb_nt;
     const int H = p.hop, N = p.n_fft, TF = p.TF;
-    const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, p.n_chunks, 1);
+    const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, p.n_chunks);
     float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
     cpx* __restrict__ twp_s = reinterpret_cast<cpx*>(smem + L.twp);
     cpx* __restrict__ twn_s = reinterpret_cast<cpx*>(smem + L.twn);

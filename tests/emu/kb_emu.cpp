@@ -13,7 +13,7 @@
 
 template <int Q, int MODE>
 static void run_stft_qm(const KbStftParams& p, int n_cta) {
-    const KbStftSmem L = kb_stft_smem_layout(Q, p.n_fft, p.hop, p.TF, p.n_warps, p.mode, p.n_bands, p.n_chunks, 1);
+    const KbStftSmem L = kb_stft_smem_layout(Q, p.n_fft, p.hop, p.TF, p.n_warps, p.mode, p.n_bands, p.n_chunks);
     std::vector<char> raw(L.total + 64 + 16);
     char* smem = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
     for (int cta = 0; cta < n_cta; ++cta) {
