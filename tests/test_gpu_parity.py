@@ -526,8 +526,8 @@ def test_more_than_2_31_elements(K):
     B, L = 8192, 270000
     assert B * L > 2 ** 31
     free, _ = torch.cuda.mem_get_info()
-    if free < 16 * 2 ** 30:
-        pytest.skip('needs 16 GB of free device memory')
+    if free < 64 * 2 ** 30:
+        pytest.skip('needs 64 GB of free device memory (8.9 GB input, 35 GB complex output, copies)')
     layer = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=16000, n_mels=128, return_decibel=True,
                                        input_data_format='channels_last', output_data_format='channels_last')
     x = torch.empty((B, L, 1), device='cuda')
