@@ -687,6 +687,9 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     cudaStream_t st = (cudaStream_t)stream;
     const int B = xd->batch, C = xd->channels, Ln = xd->length;
     if (B < 0 || C < 0 || Ln < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    if (pad_begin && plan->hop > plan->n_fft)
+        return kb_fail(KAPRE_E_INVALID, "pad_begin needs hop_length <= n_fft (the padding is n_fft - hop_length = %d)",
+                       plan->n_fft - plan->hop);
     const int T = kapre_stft_num_frames(plan, Ln, pad_begin, pad_end);
     if (B == 0 || C == 0 || T <= 0) return 0;
     if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");

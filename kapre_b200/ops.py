@@ -213,6 +213,10 @@ def stft_forward(x: torch.Tensor, plan: StftPlan, input_data_format, output_data
         raise N.KapreNativeError('stft_forward needs a CUDA tensor')
     if x.dtype != torch.float32:
         x = x.float()
+    if pad_begin and plan.hop_length > plan.n_fft:
+        # kapre/time_frequency.py:169-172 pads by n_fft - hop_length; tf.pad rejects a negative amount
+        raise ValueError('pad_begin needs hop_length <= n_fft: the padding is n_fft - hop_length = %d'
+                         % (plan.n_fft - plan.hop_length))
     xd, (B, C, L) = _wave_desc(x, input_data_format)
     T = plan.num_frames(L, pad_begin, pad_end)
     fbmode = mode in (N.OUT_FB, N.OUT_FB_DB)

@@ -160,6 +160,8 @@ def stft_layer(x, n_fft=2048, win_length=None, hop_length=None, window_name=None
     if idf == CH_LAST:
         x = np.transpose(x, (0, 2, 1))  # :164-167
     if pad_begin:
+        if hop_length > n_fft:   # tf.pad rejects negative paddings (InvalidArgumentError in the reference)
+            raise ValueError('pad_begin needs hop_length <= n_fft: the padding is n_fft - hop_length = %d' % (n_fft - hop_length))
         x = np.pad(x, [(0, 0), (0, 0), (int(n_fft - hop_length), 0)])  # :169-172 (n_fft, not win)
     window = get_window(window_name, win_length, dtype=dtype)
     s = stft_frames(x, n_fft, win_length, hop_length, window, pad_end, dtype=dtype)  # (b, c, t, f)
