@@ -580,3 +580,12 @@ def test_c_client_matches_oracle(tmp_path):
                                  output_data_format='channels_last')[..., 0]
     assert np.abs(got - ref).max() < 1e-3
     assert 'launches=4' in out.stdout          # 2 calls x (fused kernel + clamp)
+
+
+def test_pad_begin_with_hop_larger_than_n_fft_is_rejected(K):
+    """kapre pads by n_fft - hop_length (time_frequency.py:169-172); tf.pad raises on a negative amount."""
+    x = np.zeros((1, 4000, 1), dtype=np.float32)
+    with pytest.raises(ValueError):
+        K.STFT(n_fft=256, hop_length=300, pad_begin=True)(x)
+    y = K.STFT(n_fft=256, hop_length=300, pad_begin=False)(x)      # hop > n_fft itself is fine
+    assert y.shape == (1, 1 + (4000 - 256) // 300, 129, 1)
