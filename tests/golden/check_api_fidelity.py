@@ -83,6 +83,54 @@ def main(n):
         bad += compare('ApplyFilterbank', dict(type=pick(['mel', 'log', 'tri']),
                                                filterbank_kwargs=dict(sample_rate=16000, n_freq=n_fft // 2 + 1, n_mels=8),
                                                data_format=fmt_i))
+    # composed factories: same layer classes in the same order, each with the same config
+    from kapre import composed as RC
+
+    def layer_list(model):
+        out = []
+        for lay in model.layers:
+            cfg = lay.get_config()
+            for k in ('name', 'trainable', 'dtype'):
+                cfg.pop(k, None)
+            cfg = dict((k, (np.asarray(v).shape if hasattr(v, 'shape') else v)) for k, v in cfg.items())
+            out.append((type(lay).__name__, cfg))
+        return out
+
+    for _ in range(max(10, n // 5)):
+        kw = dict(n_fft=pick([256, 512, 1024]), win_length=pick([None, 200]), hop_length=pick([None, 64]),
+                  window_name=pick([None, 'hamming_window']), pad_begin=flip(), pad_end=flip(),
+                  return_decibel=flip(), db_amin=pick([1e-5, 1e-7]), db_ref_value=pick([1.0, 0.5]),
+                  db_dynamic_range=pick([80.0, 50.0]), input_data_format=pick(['channels_first', 'channels_last', 'default']),
+                  output_data_format=pick(['channels_first', 'channels_last', 'default']))
+        for fn, extra in (('get_stft_magnitude_layer', {}),
+                          ('get_melspectrogram_layer', dict(sample_rate=pick([16000, 22050]), n_mels=pick([40, 128]),
+                                                            mel_f_min=pick([0.0, 30.0]), mel_f_max=pick([None, 7000.0]),
+                                                            mel_htk=flip(), mel_norm=pick(['slaney', None]))),
+                          ('get_log_frequency_spectrogram_layer', dict(sample_rate=22050, log_n_bins=pick([48, 84]),
+                                                                       log_f_min=pick([None, 55.0]),
+                                                                       log_bins_per_octave=pick([12, 24]),
+                                                                       log_spread=pick([0.125, 0.25])))):
+            a = layer_list(getattr(RC, fn)(**dict(kw, **extra)))
+            b = layer_list(getattr(M, fn)(**dict(kw, **extra)))
+            if a != b:
+                print('factory differs:', fn, dict(kw, **extra), a, b)
+                bad += 1
+    # filterbank matrices: the reference's backend functions (librosa restated in the stand-in) vs this repository's
+    from kapre import backend as RB
+    for _ in range(20):
+        sr, n_freq = pick([8000, 16000, 44100]), pick([129, 257, 513])
+        kw = dict(sample_rate=sr, n_freq=n_freq, n_mels=pick([10, 40, 96]), f_min=pick([0.0, 50.0]),
+                  f_max=pick([None, sr / 2.5]), htk=flip(), norm=pick(['slaney', None]))
+        a, b = np.asarray(RB.filterbank_mel(**kw)), np.asarray(M.backend.filterbank_mel(**kw))
+        if a.shape != b.shape or np.abs(a - b).max() > 2e-6 * max(1.0, np.abs(a).max()):
+            print('filterbank_mel differs:', kw)
+            bad += 1
+        kw = dict(sample_rate=sr, n_freq=n_freq, n_bins=pick([24, 60]), bins_per_octave=pick([12, 24]),
+                  f_min=pick([None, 40.0]), spread=pick([0.125, 0.3]))
+        a, b = np.asarray(RB.filterbank_log(**kw)), np.asarray(M.backend.filterbank_log(**kw))
+        if a.shape != b.shape or np.abs(a - b).max() > 2e-6 * max(1.0, np.abs(a).max()):
+            print('filterbank_log differs:', kw)
+            bad += 1
     print('api fidelity: %d keyword sets per layer, %d disagreements' % (n, bad))
     return bad
 
