@@ -41,11 +41,13 @@ class Frame(Layer):
     def call(self, x):
         return ops.frame(x, self.frame_length, self.hop_length, self.pad_end, self.pad_value, self.data_format)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({'frame_length': self.frame_length, 'hop_length': self.hop_length, 'pad_end': self.pad_end,
-                       'pad_value': self.pad_value, 'data_format': self.data_format_str})
-        return config
+    _config_fields = (
+        ('frame_length', 'frame_length'),
+        ('hop_length', 'hop_length'),
+        ('pad_end', 'pad_end'),
+        ('pad_value', 'pad_value'),
+        ('data_format', 'data_format_str'),
+    )
 
 
 @register_keras_serializable(package='Kapre')
@@ -70,12 +72,15 @@ class Energy(Layer):
         return ops.energy(x, self.frame_length, self.hop_length, self.pad_end, self.pad_value, nor_coeff,
                           self.data_format)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({'sample_rate': self.sample_rate, 'ref_duration': self.ref_duration,
-                       'frame_length': self.frame_length, 'hop_length': self.hop_length, 'pad_end': self.pad_end,
-                       'pad_value': self.pad_value, 'data_format': self.data_format_str})
-        return config
+    _config_fields = (
+        ('sample_rate', 'sample_rate'),
+        ('ref_duration', 'ref_duration'),
+        ('frame_length', 'frame_length'),
+        ('hop_length', 'hop_length'),
+        ('pad_end', 'pad_end'),
+        ('pad_value', 'pad_value'),
+        ('data_format', 'data_format_str'),
+    )
 
 
 def dct2_htk_matrix(n_mels: int, n_mfccs: int) -> np.ndarray:
@@ -110,7 +115,4 @@ class LogmelToMFCC(Layer):
             fb = self._fb[n_mels] = ops.Filterbank(dct2_htk_matrix(n_mels, min(self.n_mfccs, n_mels)))
         return ops.apply_filterbank(log_melgrams, fb, self.data_format)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({'n_mfccs': self.n_mfccs, 'data_format': self.data_format_str})
-        return config
+    _config_fields = (('n_mfccs', 'n_mfccs'), ('data_format', 'data_format_str'))

@@ -85,8 +85,14 @@ class Layer:
         return 0
 
     # -- serialisation ------------------------------------------------------------------
+    # constructor keywords a subclass reports in get_config(): (config key, attribute holding the value)
+    _config_fields = ()
+
     def get_config(self):
-        return {'name': self.name, 'trainable': self.trainable, 'dtype': self.dtype}
+        config = {'name': self.name, 'trainable': self.trainable, 'dtype': self.dtype}
+        for key, attr in self._config_fields:
+            config[key] = getattr(self, attr)
+        return config
 
     @classmethod
     def from_config(cls, config):
@@ -149,19 +155,16 @@ class STFT(Layer):
         return ops.stft_forward(x, self.plan, self.input_data_format, self.output_data_format,
                                 self.pad_begin, self.pad_end, N.OUT_COMPLEX)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({
-            'n_fft': self.n_fft,
-            'win_length': self.win_length,
-            'hop_length': self.hop_length,
-            'window_name': self.window_name,
-            'pad_begin': self.pad_begin,
-            'pad_end': self.pad_end,
-            'input_data_format': self.input_data_format_original,
-            'output_data_format': self.output_data_format_original,
-        })
-        return config
+    _config_fields = (
+        ('n_fft', 'n_fft'),
+        ('win_length', 'win_length'),
+        ('hop_length', 'hop_length'),
+        ('window_name', 'window_name'),
+        ('pad_begin', 'pad_begin'),
+        ('pad_end', 'pad_end'),
+        ('input_data_format', 'input_data_format_original'),
+        ('output_data_format', 'output_data_format_original'),
+    )
 
 
 @register_keras_serializable(package='Kapre')
@@ -207,17 +210,14 @@ class InverseSTFT(Layer):
     def call(self, x):
         return ops.istft(x, self.plan, self.input_data_format, self.output_data_format)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({
-            'n_fft': self.n_fft,
-            'win_length': self.win_length,
-            'hop_length': self.hop_length,
-            'forward_window_name': self.forward_window_name,
-            'input_data_format': self.input_data_format_original,
-            'output_data_format': self.output_data_format_original,
-        })
-        return config
+    _config_fields = (
+        ('n_fft', 'n_fft'),
+        ('win_length', 'win_length'),
+        ('hop_length', 'hop_length'),
+        ('forward_window_name', 'forward_window_name'),
+        ('input_data_format', 'input_data_format_original'),
+        ('output_data_format', 'output_data_format_original'),
+    )
 
 
 @register_keras_serializable(package='Kapre')
@@ -241,10 +241,7 @@ class Phase(Layer):
     def call(self, x):
         return ops.phase(x)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({'approx_atan_accuracy': self.approx_atan_accuracy})
-        return config
+    _config_fields = (('approx_atan_accuracy', 'approx_atan_accuracy'),)
 
 
 @register_keras_serializable(package='Kapre')
@@ -262,10 +259,7 @@ class MagnitudeToDecibel(Layer):
         return backend.magnitude_to_decibel(x, ref_value=self.ref_value, amin=self.amin,
                                             dynamic_range=self.dynamic_range)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({'amin': self.amin, 'dynamic_range': self.dynamic_range, 'ref_value': self.ref_value})
-        return config
+    _config_fields = (('amin', 'amin'), ('dynamic_range', 'dynamic_range'), ('ref_value', 'ref_value'))
 
 
 @register_keras_serializable(package='Kapre')
@@ -298,11 +292,11 @@ class ApplyFilterbank(Layer):
     def call(self, x):
         return ops.apply_filterbank(x, self.fb, self.data_format)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({'type': self.type, 'filterbank_kwargs': self.filterbank_kwargs,
-                       'data_format': self.data_format_original})
-        return config
+    _config_fields = (
+        ('type', 'type'),
+        ('filterbank_kwargs', 'filterbank_kwargs'),
+        ('data_format', 'data_format_original'),
+    )
 
 
 @register_keras_serializable(package='Kapre')
@@ -332,7 +326,4 @@ class Delta(Layer):
     def call(self, x):
         return ops.delta(x, self.win_length, self.mode, self.data_format)
 
-    def get_config(self):
-        config = super().get_config()
-        config.update({'win_length': self.win_length, 'mode': self.mode, 'data_format': self.data_format_original})
-        return config
+    _config_fields = (('win_length', 'win_length'), ('mode', 'mode'), ('data_format', 'data_format_original'))
