@@ -3,6 +3,7 @@
 // loop over the CTA's threads; lets `pytest -m "not gpu"` validate the index arithmetic of
 // the fused kernels against the oracle in a container that has no GPU.
 #define KB_HOST_EMU 1
+#include <cmath>
 #include <cstdlib>
 #include <cstdio>
 #include <vector>
@@ -10,6 +11,7 @@
 #include "../../kapre_b200/csrc/stft_core.cuh"
 #include "../../kapre_b200/csrc/stft_mc_core.cuh"
 #include "../../kapre_b200/csrc/istft_core.cuh"
+#include "../../kapre_b200/csrc/aux_core.cuh"
 
 template <int Q, int MODE>
 static void run_stft_qm(const KbStftParams& p, int n_cta) {
@@ -207,6 +209,75 @@ int kb_emu_istft(const float* X, long long x_sb, long long x_sc, long long x_st,
         case 8: run_istft<8>(p, n_cta); break;
         case 16: run_istft<16>(p, n_cta); break;
         case 32: run_istft<32>(p, n_cta); break;
+    }
+    return 0;
+}
+
+
+// ---- stand-alone / generic-n_fft kernel bodies (aux_core.cuh) -----------------------------------
+int kb_emu_dft(const float* x, long long x_sb, long long x_sc, long long x_sl, int B, int C, int L,
+               int n_fft, int win_length, int hop, int pad_left, int T, const float* window, int mode,
+               void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk, int n_cta) {
+    const int win_eff = win_length < n_fft ? win_length : n_fft;
+    std::vector<float2> tw(n_fft);
+    for (int r = 0; r < n_fft; ++r) {
+        const double a = -2.0 * M_PI * (double)r / (double)n_fft;
+        tw[r] = make_float2((float)cos(a), (float)sin(a));
+    }
+    KbDftParams p{};
+    p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
+    p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left; p.win_eff = win_eff; p.w = window; p.tw = tw.data();
+    p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
+    p.n_tiles_t = (T + KB_DFT_TF - 1) / KB_DFT_TF; p.n_warps = 8;
+    const KbDftSmem L_ = kb_dft_smem_layout(n_fft, win_eff);
+    std::vector<char> smem(L_.total + 64);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(smem.begin(), smem.end(), (char)0x7f);
+        kb_dft_cta(p, smem.data(), cta, n_cta);
+    }
+    return 0;
+}
+
+int kb_emu_idft(const float* X, long long x_sb, long long x_sc, long long x_st, long long x_sk, int B, int C, int T,
+                int n_fft, int win_length, int hop, const float* dual_window, float* y, long long y_sb,
+                long long y_sc, long long y_sl, int n_cta) {
+    const int win = win_length < n_fft ? win_length : n_fft;
+    std::vector<float> dn(win);
+    for (int m = 0; m < win; ++m) dn[m] = (float)((double)dual_window[m] / (double)n_fft);
+    std::vector<float2> tw(n_fft);
+    for (int r = 0; r < n_fft; ++r) {
+        const double a = 2.0 * M_PI * (double)r / (double)n_fft;
+        tw[r] = make_float2((float)cos(a), (float)sin(a));
+    }
+    KbIdftParams p{};
+    p.X = (const float2*)X; p.x_sb = x_sb; p.x_sc = x_sc; p.x_st = x_st; p.x_sk = x_sk;
+    p.B = B; p.C = C; p.T = T; p.n_fft = n_fft; p.hop = hop; p.win = win;
+    p.out_len = (T - 1) * hop + win_length; p.dualn = dn.data(); p.tw = tw.data();
+    p.y = y; p.y_sb = y_sb; p.y_sc = y_sc; p.y_sl = y_sl;
+    p.n_warps = 8; p.n_tiles_s = (p.out_len + 255) / 256;
+    std::vector<char> smem((size_t)n_fft * 8 + 64);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(smem.begin(), smem.end(), (char)0x7f);
+        kb_idft_cta(p, smem.data(), cta, n_cta);
+    }
+    return 0;
+}
+
+int kb_emu_fb(const float* x, long long x_sb, long long x_sc, long long x_st, long long x_sk, int B, int C, int T,
+              const float* fb, int n_freq, int n_bands, float* out, long long o_sb, long long o_sc, long long o_st,
+              long long o_sk, int n_cta) {
+    std::vector<KbBand> bands; std::vector<float> fbw;
+    kb_make_bands(fb, n_freq, n_bands, bands, fbw);
+    KbFbParams p{};
+    p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_st = x_st; p.x_sk = x_sk; p.B = B; p.C = C; p.T = T; p.F = n_freq;
+    p.bands = bands.data(); p.fbw = fbw.data(); p.n_bands = n_bands;
+    p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk;
+    p.n_tiles_t = (T + 31) / 32; p.n_warps = 8;
+    const KbFbSmem L_ = kb_fb_smem_layout(n_freq, n_bands);
+    std::vector<char> smem(L_.total + 64);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(smem.begin(), smem.end(), (char)0x7f);
+        kb_fb_cta(p, smem.data(), cta, n_cta);
     }
     return 0;
 }

@@ -143,3 +143,78 @@ def emu_istft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, TFc=16, n
                           _fp(dual), _fp(y), LL(ysb), LL(ysc), LL(ysl), TFc, n_warps, n_cta)
     assert rc == 0
     return y
+
+
+def _strides4(shape, fmt):
+    """(shape of the array, element strides (b, c, t, k)) of a (B, C, T, K) tensor in `fmt`."""
+    B, C, T, K = shape
+    if fmt == 'channels_last':
+        return (B, T, K, C), (T * K * C, 1, K * C, C)
+    return (B, C, T, K), (C * T * K, T * K, K, 1)
+
+
+def emu_dft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, out_fmt, n_cta=3):
+    """Generic-n_fft forward kernel body (aux_core.cuh kb_dft_cta): complex or magnitude output."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if in_fmt == 'channels_last':
+        B, L, C = x.shape
+        sb, sl, sc = L * C, C, 1
+    else:
+        B, C, L = x.shape
+        sb, sc, sl = C * L, L, 1
+    pad_left = (n_fft - hop) if pad_begin else 0
+    Lp = L + pad_left
+    T = -(-Lp // hop) if pad_end else max(0, 1 + (Lp - win_length) // hop)
+    shape, (osb, osc, ost, osk) = _strides4((B, C, T, n_fft // 2 + 1), out_fmt)
+    out = np.full(shape, np.nan, dtype=np.complex64 if mode == MODE_COMPLEX else np.float32)
+    window = np.ascontiguousarray(window, dtype=np.float32)
+    LL = ctypes.c_longlong
+    rc = lib.kb_emu_dft(_fp(x), LL(sb), LL(sc), LL(sl), B, C, L, n_fft, win_length, hop, pad_left, T, _fp(window),
+                        mode, _fp(out), LL(osb), LL(osc), LL(ost), LL(osk), n_cta)
+    assert rc == 0
+    return out
+
+
+def emu_idft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, n_cta=3):
+    """Generic-n_fft inverse kernel body (kb_idft_cta)."""
+    lib = load()
+    X = np.ascontiguousarray(X, dtype=np.complex64)
+    if in_fmt == 'channels_last':
+        B, T, F, C = X.shape
+    else:
+        B, C, T, F = X.shape
+    _, (sb, sc, st, sk) = _strides4((B, C, T, F), in_fmt)
+    out_len = (T - 1) * hop + win_length
+    if out_fmt == 'channels_last':
+        y = np.full((B, out_len, C), np.nan, dtype=np.float32)
+        ysb, ysl, ysc = out_len * C, C, 1
+    else:
+        y = np.full((B, C, out_len), np.nan, dtype=np.float32)
+        ysb, ysc, ysl = C * out_len, out_len, 1
+    dual = np.ascontiguousarray(dual_window, dtype=np.float32)
+    LL = ctypes.c_longlong
+    rc = lib.kb_emu_idft(_fp(X), LL(sb), LL(sc), LL(st), LL(sk), B, C, T, n_fft, win_length, hop, _fp(dual), _fp(y),
+                         LL(ysb), LL(ysc), LL(ysl), n_cta)
+    assert rc == 0
+    return y
+
+
+def emu_fb(x, fb, fmt, n_cta=3):
+    """Stand-alone ApplyFilterbank kernel body (kb_fb_cta) on a (B, T, F, C) / (B, C, T, F) float tensor."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if fmt == 'channels_last':
+        B, T, F, C = x.shape
+    else:
+        B, C, T, F = x.shape
+    _, (sb, sc, st, sk) = _strides4((B, C, T, F), fmt)
+    fb = np.ascontiguousarray(fb, dtype=np.float32)
+    M = fb.shape[1]
+    shape, (osb, osc, ost, osk) = _strides4((B, C, T, M), fmt)
+    out = np.full(shape, np.nan, dtype=np.float32)
+    LL = ctypes.c_longlong
+    rc = lib.kb_emu_fb(_fp(x), LL(sb), LL(sc), LL(st), LL(sk), B, C, T, _fp(fb), fb.shape[0], M, _fp(out), LL(osb),
+                       LL(osc), LL(ost), LL(osk), n_cta)
+    assert rc == 0
+    return out

@@ -120,3 +120,29 @@ def test_fuzz_filterbank_modes(n_fft, hop, L, C, n_mels, htk, pad_end, ifmt, ofm
     ref_db = 10.0 * np.log10(np.maximum(ref, 1e-5))
     assert np.abs(out - ref_db).max() < 2e-3
     assert np.allclose(item_max, np.maximum(ref, 1e-5).reshape(2, -1).max(axis=1), rtol=5e-6)
+
+
+@settings(**COMMON)
+@given(n_fft=st.integers(2, 130), win_frac=st.sampled_from([1.0, 0.6]), hop=st.integers(1, 90), L=st.integers(1, 700),
+       C=st.integers(1, 3), pad_begin=st.booleans(), pad_end=st.booleans(), fmt=FMT, seed=st.integers(0, 10 ** 6))
+def test_fuzz_generic_n_fft(n_fft, win_frac, hop, L, C, pad_begin, pad_end, fmt, seed):
+    """Direct-DFT bodies (any n_fft, even or odd): forward against the oracle, then the inverse of that spectrum."""
+    win = max(1, int(n_fft * win_frac))
+    if pad_begin and hop > n_fft:
+        return
+    x = _wave(seed, 2, C, L, fmt)
+    w = O.get_window(None, win).astype(np.float32)
+    ref = O.stft_layer(x, n_fft, win, hop, None, pad_begin, pad_end, fmt, fmt)
+    if ref.size == 0:
+        return
+    out = E.emu_dft(x, n_fft, win, hop, w, pad_begin, pad_end, E.MODE_COMPLEX, fmt, fmt, n_cta=1 + seed % 3)
+    assert out.shape == ref.shape
+    assert _nerr(out, ref) < 5e-6
+    if hop <= win:                  # the dual window needs overlapping (or abutting) frames
+        dual = O.inverse_stft_window(win, hop, O.get_window(None, win))
+        if np.isfinite(dual).all() and np.abs(dual).max() < 20:      # barely overlapping frames: 1/w blows up round-off
+            spec = ref.astype(np.complex64)
+            want = O.istft_layer(spec, n_fft, win, hop, None, fmt, fmt)
+            y = E.emu_idft(spec, n_fft, win, hop, dual, fmt, fmt, n_cta=1 + seed % 2)
+            assert y.shape == want.shape
+            assert _nerr(y, want) < 2e-5       # fp32 sums of n_fft terms, times a dual window of up to 20

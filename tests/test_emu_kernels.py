@@ -196,3 +196,43 @@ def test_emu_sixteen_warp_cta_n2048_mel():
                                fb=fb, TF=16, n_warps=16, n_cta=3)
     assert np.abs(out - 10.0 * np.log10(np.maximum(ref, 1e-5))).max() < 1e-3
     assert np.allclose(item_max, np.maximum(ref, 1e-5).reshape(2, -1).max(axis=1), rtol=3e-6)
+
+
+# ------------------------------------------------------------------------------- stand-alone / generic-n_fft bodies
+@pytest.mark.parametrize('n_fft,win,hop', [(1000, 1000, 250), (1000, 512, 250), (400, 400, 160), (100, 64, 33), (6, 6, 2)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_emu_generic_n_fft_forward_and_inverse(n_fft, win, hop, fmt):
+    """aux_core.cuh: direct DFT / inverse DFT for n_fft outside {256..2048} (the reference's tests use 1000)."""
+    rng = np.random.default_rng(n_fft + hop)
+    x = wave(rng, 2, 2, 3000 if n_fft > 50 else 200, fmt)
+    w = O.get_window(None, win).astype(np.float32)
+    for pads in ((False, False), (True, True)):
+        ref = O.stft_layer(x, n_fft, win, hop, None, pads[0], pads[1], fmt, fmt)
+        out = E.emu_dft(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_COMPLEX, fmt, fmt)
+        assert out.shape == ref.shape and nerr(out, ref) < 3e-6
+        mag = E.emu_dft(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_MAG, fmt, fmt, n_cta=2)
+        assert nerr(mag, np.abs(ref)) < 3e-6
+    spec = O.stft_layer(x, n_fft, win, hop, None, True, True, fmt, fmt).astype(np.complex64)
+    dual = O.inverse_stft_window(win, hop, O.get_window(None, win))
+    ref = O.istft_layer(spec, n_fft, win, hop, None, fmt, fmt)
+    y = E.emu_idft(spec, n_fft, win, hop, dual, fmt, fmt)
+    assert y.shape == ref.shape and nerr(y, ref) < 3e-6
+
+
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('F,M,kind', [(257, 40, 'mel'), (513, 128, 'mel'), (501, 24, 'mel'), (257, 84, 'log'), (129, 7, 'dense')])
+def test_emu_standalone_filterbank(fmt, F, M, kind):
+    """kb_fb_cta (ApplyFilterbank on its own): banded mel, overlapping log-frequency bands, a dense matrix."""
+    rng = np.random.default_rng(F + M)
+    if kind == 'mel':
+        fb = O.filterbank_mel(16000, F, M, 0.0, None, False, 'slaney')
+    elif kind == 'log':
+        fb = O.filterbank_log(22050, F, M, 12, None, 0.125)
+    else:
+        fb = rng.normal(size=(F, M))
+    shape = (2, 45, F, 3) if fmt == 'channels_last' else (2, 3, 45, F)
+    x = np.abs(rng.normal(size=shape)).astype(np.float32)
+    ref = O.apply_filterbank(x, fb, fmt)
+    out = E.emu_fb(x, fb, fmt)
+    assert out.shape == ref.shape
+    assert nerr(out, ref) < 2e-6
