@@ -310,7 +310,8 @@ def inverse_stft_window(win_length, hop, forward_window):
     den[:win_length] = w ** 2
     den = den.reshape(overlaps, hop).sum(0, keepdims=True)
     den = np.tile(den, (overlaps, 1)).reshape(overlaps * hop)
-    return w / den[:win_length]
+    with np.errstate(divide='ignore', invalid='ignore'):     # zero window samples give inf / nan, as in TF
+        return w / den[:win_length]
 
 
 def inverse_stft_frames(stfts, n_fft, win_length, hop, dual_window, dtype=np.float64):
