@@ -152,8 +152,9 @@ int kapre_version(void);
 uint64_t kapre_launch_count(void);
 /* Name of the last fused-forward launch configuration, e.g. "Q16 TF16 NW4 grid296 smem98304". */
 const char* kapre_last_launch_info(void);
-/* Kernel timing for bench.py's roofline: when enabled, every fused forward / inverse kernel
- * launch is bracketed by CUDA events on its own stream.  kapre_profile_read synchronises with
+/* Kernel timing for bench.py's roofline: enable = n > 0 brackets every n-th fused forward / inverse
+ * kernel launch by CUDA events on its own stream (n = 1: every launch; a stride leaves the other
+ * launches free to overlap their predecessor through programmatic dependent launch); 0 = off.  kapre_profile_read synchronises with
  * the recorded events, adds their durations to *total_ms / *launches and clears the list. */
 int kapre_profile_enable(int enable);
 int kapre_profile_read(double* total_ms, uint64_t* launches);

@@ -99,8 +99,9 @@ def last_launch_info() -> str:
     return s.decode() if s else ''
 
 
-def profile_enable(on: bool):
-    lib().kapre_profile_enable(1 if on else 0)
+def profile_enable(on, every: int = 1):
+    """Bracket every `every`-th launch of the dominant kernels with CUDA events (0 / False: off)."""
+    lib().kapre_profile_enable(int(every) if on else 0)
 
 
 def profile_read():

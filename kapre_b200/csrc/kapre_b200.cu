@@ -30,14 +30,19 @@ static std::atomic<uint64_t> g_launches{0};
 // optional kernel timing (bench.py roofline): event pairs around the dominant kernels
 #include <mutex>
 static std::mutex g_prof_mu;
-static bool g_prof_on = false;
+static int g_prof_on = 0;             // 0: off, n: every n-th dominant-kernel launch is bracketed by events
+static std::atomic<uint64_t> g_prof_seq{0};
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 
 struct KbProfScope {
     cudaStream_t st;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     explicit KbProfScope(cudaStream_t s) : st(s) {
-        if (!g_prof_on) return;
+        const int every = g_prof_on;
+        if (!every) return;
+        // sampling: an event record between two kernels serialises them (no programmatic dependent
+        // launch across it), so a stride > 1 leaves most launches of a timed loop undisturbed
+        if ((g_prof_seq++ % (uint64_t)every) != 0) return;
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
         cudaEventRecord(e0, st);
     }
@@ -131,6 +136,7 @@ __global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size, l
                                    unsigned int* __restrict__ item_max, float amin,
                                    float db_mul, float db_sub, float dyn_range) {
 #if __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.launch_dependents;");   // the next fused kernel may start its table prologue
     cudaGridDependencySynchronize();
 #endif
     const long long item = blockIdx.x;
@@ -315,6 +321,10 @@ struct kapre_filterbank {
     kb_f4* cw = nullptr;
     kb_i2* cm = nullptr;
     int* cg = nullptr;
+    int n_msteps = 0;          // tensor-core form (kb_make_fb_mma) for the fused kernel
+    kb_f4* mw = nullptr;
+    kb_i2* ms = nullptr;
+    int* mg = nullptr;
 };
 
 static int kb_env_int(const char* name, int dflt) {
@@ -326,13 +336,16 @@ static int kb_env_int(const char* name, int dflt) {
 // launch configuration of the fused forward kernel
 // ------------------------------------------------------------------------------------------
 struct FwdCfg { int TF, NW, smem, bps; };
+#ifndef KB_FBMMA_DEFAULT
+#define KB_FBMMA_DEFAULT 0
+#endif
 
 // Tile shape of the fused forward kernel.  Measured on B200 (profiles/): the kernel is
 // latency-bound, so resident warps per SM (up to the 16 the 128-register kernel allows) matter
 // most, then larger tiles (less re-staging of the hop overlap).  Filterbank modes keep the
 // tile's magnitudes in the warps' exchange regions, which needs TF == frames per round.
 static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int mode, int n_bands, int n_chunks,
-                            FwdCfg* out) {
+                            int fbmma, FwdCfg* out) {
     const int FPW = 32 / Q;
     const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     const int force_tf = kb_env_int("KAPRE_B200_TF", 0);
@@ -351,7 +364,7 @@ static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int m
         for (int TF = 32; TF >= 1; TF >>= 1) {
             if (fb ? (TF != FR) : (TF % FR != 0)) continue;
             if (!fb && force_tf && TF != force_tf) continue;
-            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands, n_chunks);
+            const KbStftSmem L = kb_stft_smem_layout(Q, n_fft, hop, TF, NW, mode, n_bands, n_chunks, fbmma);
             if (L.total > dev.smem_optin) continue;
             int bps = sm_smem / (L.total + 1024);
             if (bps > 16 / NW) bps = 16 / NW;                 // 128 registers per thread: 16 warps per SM
@@ -376,6 +389,25 @@ static int kb_set_smem(K kernel, int smem) {
     return 0;
 }
 
+// Launch of a kernel whose body starts with griddepcontrol.wait (kb_stft_cta): programmatic dependent
+// launch lets its table prologue overlap the tail of the previous kernel in the stream (the clamp of the
+// previous call).  Only kernels that contain the wait may be launched this way.
+template <typename Kern>
+static int kb_launch_pdl(Kern kernel, int grid, int block, int smem, cudaStream_t st, const KbStftParams& p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = kb_env_int("KAPRE_B200_PDL_FWD", 1) ? 1 : 0;
+    KB_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+    return 0;
+}
+
 template <int Q, int MODE>
 static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStream_t st) {
     if (p.n_warps > KB_MAX_WARPS) {
@@ -383,8 +415,7 @@ static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStre
             int rc = kb_set_smem(kb_stft_kernel_w16<Q, MODE>, smem);
             if (rc) return rc;
             KbProfScope prof(st);
-            kb_stft_kernel_w16<Q, MODE><<<grid, p.n_warps * 32, smem, st>>>(p);
-            KB_CUDA(cudaGetLastError());
+            if ((rc = kb_launch_pdl(kb_stft_kernel_w16<Q, MODE>, grid, p.n_warps * 32, smem, st, p))) return rc;
             g_launches++;
             return 0;
         } else {
@@ -394,8 +425,7 @@ static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStre
     int rc = kb_set_smem(kb_stft_kernel<Q, MODE>, smem);
     if (rc) return rc;
     KbProfScope prof(st);
-    kb_stft_kernel<Q, MODE><<<grid, p.n_warps * 32, smem, st>>>(p);
-    KB_CUDA(cudaGetLastError());
+    if ((rc = kb_launch_pdl(kb_stft_kernel<Q, MODE>, grid, p.n_warps * 32, smem, st, p))) return rc;
     g_launches++;
     return 0;
 }
@@ -588,7 +618,8 @@ const char* kapre_last_launch_info(void) { return g_launch_info.c_str(); }
 
 int kapre_profile_enable(int enable) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    g_prof_on = enable != 0;
+    g_prof_on = enable > 0 ? enable : 0;
+    g_prof_seq = 0;
     return 0;
 }
 
@@ -738,8 +769,10 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     const bool bulk = (xd->stride_l == 1) && (((uintptr_t)x_dev & 3) == 0) && xd->stride_b >= 0 && xd->stride_c >= 0 &&
                       kb_env_int("KAPRE_B200_NOBULK", 0) == 0;
     FwdCfg cfg;
+    // filterbank phase on the tensor pipe (mma.sync 3xTF32) or on the CUDA cores (chunk lists)
+    const int fbmma = (fbmode && fb->mw && kb_env_int("KAPRE_B200_FBMMA", KB_FBMMA_DEFAULT)) ? 1 : 0;
     if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0,
-                         fbmode ? fb->n_chunks : 0, &cfg))
+                         fbmode ? (fbmma ? fb->n_msteps : fb->n_chunks) : 0, fbmma, &cfg))
         return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
                        plan->n_fft, plan->hop, fbmode ? fb->n_bands : 0);
     KbStftParams p{};
@@ -754,6 +787,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if (fbmode) {
         p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands; p.n_fbw = fb->n_w;
         p.cw = fb->cw; p.cm = fb->cm; p.cg = fb->cg; p.n_chunks = fb->n_chunks;
+        p.mw = fb->mw; p.ms = fb->ms; p.mg = fb->mg; p.n_msteps = fb->n_msteps;
     }
     if (dbmode) {
         p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev;
@@ -806,6 +840,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         }
     } else {
         p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
+        p.fb_mma = fbmma;
         tiles = (long long)B * C * p.n_tiles_t;
         if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
         const long long gmax = (long long)plan->dev.sm_count * cfg.bps;
@@ -821,8 +856,8 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if (rc) return rc;
     {
         char buf[160];
-        snprintf(buf, sizeof(buf), "%sQ%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld", use_mc ? "MC " : "", plan->Q,
-                 cfg.TF, cfg.NW, use_mc ? 0 : (int)bulk, grid, cfg.smem, cfg.bps, tiles);
+        snprintf(buf, sizeof(buf), "%sQ%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld fbmma%d", use_mc ? "MC " : "", plan->Q,
+                 cfg.TF, cfg.NW, use_mc ? 0 : (int)bulk, grid, cfg.smem, cfg.bps, tiles, use_mc ? 0 : fbmma);
         g_launch_info = buf;
     }
     if (dbmode) {
@@ -975,6 +1010,12 @@ int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre
         if ((rc = kb_upload(cw, &f->cw)) || (rc = kb_upload(cm, &f->cm)) || (rc = kb_upload(cg, &f->cg))) {
             kapre_filterbank_destroy(f); return rc;
         }
+        std::vector<kb_f4> mw; std::vector<kb_i2> ms; std::vector<int> mg;
+        kb_make_fb_mma(fb_host, n_freq, n_bands, mw, ms, mg);
+        f->n_msteps = (int)ms.size();
+        if ((rc = kb_upload(mw, &f->mw)) || (rc = kb_upload(ms, &f->ms)) || (rc = kb_upload(mg, &f->mg))) {
+            kapre_filterbank_destroy(f); return rc;
+        }
     }
     *out = f;
     return 0;
@@ -983,6 +1024,7 @@ int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre
 void kapre_filterbank_destroy(kapre_filterbank* f) {
     if (!f) return;
     cudaFree(f->bands); cudaFree(f->w); cudaFree(f->cw); cudaFree(f->cm); cudaFree(f->cg);
+    cudaFree(f->mw); cudaFree(f->ms); cudaFree(f->mg);
     delete f;
 }
 

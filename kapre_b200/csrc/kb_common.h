@@ -82,6 +82,13 @@ struct KbStftParams {
     const kb_i2* cm;
     const int* cg;
     int n_chunks;
+    // tensor-core form (kb_make_fb_mma): fb_mma = 1 runs the filterbank phase as a block-banded
+    // mma.sync m16n8k8 3xTF32 GEMM; mw is read from global memory (L2-resident), ms / mg are staged.
+    int fb_mma;
+    const kb_f4* mw;
+    const kb_i2* ms;
+    const int* mg;
+    int n_msteps;
     // decibel (modes *_DB): y = db_mul * log2(max(v, amin)) - db_sub; per-item max of max(v, amin)
     float amin, db_mul, db_sub;
     int db_ftz;              // amin >= FLT_MIN: every clamped value is a normal float, log2 may flush denormals

@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include "kb_common.h"
 
@@ -154,6 +155,103 @@ static inline void kb_make_fb_chunks(const float* fb, int n_freq, int n_bands, i
         }
     }
     cg[groups] = (int)cw.size();
+}
+
+// Tensor-core form of the filterbank for the fused kernel (mma.sync m16n8k8, 3xTF32 split): the
+// (frames x bins) . (bins x bands) product is tiled into 8-band column tiles; tile j only needs the
+// k-steps (8 bins each) its bands' supports touch (block-banded GEMM: ~17 % of the dense tile grid for a
+// 128-band Slaney mel bank).  A job = one column tile and a run of consecutive k-steps; a tile with
+// many k-steps is cut into two jobs so that the 16 job slots (dealt longest-first) stay balanced --
+// both halves then add their partial sums into the zeroed output tile (two addends: order-independent).
+//   mw[step*32 + lane] = B fragment of the step for that lane, pre-split: (b0_hi, b1_hi, b0_lo, b1_lo)
+//                        b0 = fb[k0 + t][8j + g], b1 = fb[k0 + t + 4][8j + g], g = lane / 4, t = lane % 4
+//   ms[step] = (k0, j if this is the job's last step else -1);  slot s owns steps [mg[s], mg[s+1])
+#define KB_MMA_SLOTS 16
+static inline float kb_tf32_hi(float v) {
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    u &= 0xffffe000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+static inline void kb_make_fb_mma(const float* fb, int n_freq, int n_bands, std::vector<kb_f4>& mw,
+                                  std::vector<kb_i2>& ms, std::vector<int>& mg) {
+    struct Job { int j, s0, s1; };   // column tile, k-steps [s0, s1)
+    const int n_tiles = (n_bands + 7) / 8;
+    std::vector<Job> jobs;
+    int total = 0;
+    std::vector<Job> whole;
+    for (int j = 0; j < n_tiles; ++j) {
+        int lo = n_freq, hi = 0;
+        for (int k = 0; k < n_freq; ++k)
+            for (int m = 8 * j; m < 8 * j + 8 && m < n_bands; ++m)
+                if (fb[(size_t)k * n_bands + m] != 0.0f) {
+                    if (k < lo) lo = k;
+                    hi = k + 1;
+                }
+        if (hi <= lo) { lo = 0; hi = 1; }   // all-zero tile: one step so that its outputs are written
+        Job w{j, lo / 8, (hi + 7) / 8};
+        whole.push_back(w);
+        total += w.s1 - w.s0;
+    }
+    const int target = (total + KB_MMA_SLOTS - 1) / KB_MMA_SLOTS;
+    for (const Job& w : whole) {
+        const int n = w.s1 - w.s0;
+        if (n > target && n >= 2) {
+            const int mid = w.s0 + (n + 1) / 2;
+            jobs.push_back(Job{w.j, w.s0, mid});
+            jobs.push_back(Job{w.j, mid, w.s1});
+        } else {
+            jobs.push_back(w);
+        }
+    }
+    std::stable_sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return (a.s1 - a.s0) > (b.s1 - b.s0); });
+    std::vector<int> load(KB_MMA_SLOTS, 0);
+    std::vector<std::vector<Job>> members(KB_MMA_SLOTS);
+    for (const Job& jb : jobs) {
+        int best = 0;
+        for (int s = 1; s < KB_MMA_SLOTS; ++s) if (load[s] < load[best]) best = s;
+        load[best] += jb.s1 - jb.s0;
+        members[best].push_back(jb);
+    }
+    // A warp of an NW-warp CTA walks slots w, w + NW, ...: place the slots so that position i (heavy,
+    // descending) pairs with position i + 8 (light, ascending).
+    std::vector<int> order(KB_MMA_SLOTS);
+    for (int s = 0; s < KB_MMA_SLOTS; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] > load[b]; });
+    std::vector<int> place(KB_MMA_SLOTS);
+    for (int i = 0; i < KB_MMA_SLOTS / 2; ++i) {
+        place[i] = order[i];
+        place[KB_MMA_SLOTS / 2 + i] = order[KB_MMA_SLOTS - 1 - i];
+    }
+    mw.clear(); ms.clear(); mg.assign(KB_MMA_SLOTS + 1, 0);
+    for (int pos = 0; pos < KB_MMA_SLOTS; ++pos) {
+        mg[pos] = (int)ms.size();
+        for (const Job& jb : members[place[pos]]) {
+            for (int s = jb.s0; s < jb.s1; ++s) {
+                const int k0 = 8 * s;
+                kb_i2 d;
+                d.x = k0;
+                d.y = (s == jb.s1 - 1) ? jb.j : -1;
+                ms.push_back(d);
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t = lane & 3;
+                    const int m = 8 * jb.j + g;
+                    float b[2];
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = k0 + t + 4 * h;
+                        b[h] = (k < n_freq && m < n_bands) ? fb[(size_t)k * n_bands + m] : 0.0f;
+                    }
+                    kb_f4 v;
+                    v.x = kb_tf32_hi(b[0]); v.y = kb_tf32_hi(b[1]);
+                    v.z = b[0] - v.x;       v.w = b[1] - v.y;
+                    mw.push_back(v);
+                }
+            }
+        }
+    }
+    mg[KB_MMA_SLOTS] = (int)ms.size();
 }
 
 // Synthesis-window table for the inverse kernel: dual[m] = w~[m] / n_fft, negated for odd m

@@ -37,14 +37,17 @@ struct KbStftSmem {
 // Per-warp exchange region: 32 x 33 complex for the FFT transpose, plus a skew so that the
 // magnitudes the filterbank phase reads from all warps' regions ([bin][frame-in-warp]) land in
 // distinct banks for distinct frame columns.
-KB_HD int kb_exw(int Q) {
+KB_HD int kb_exw(int Q, int fbmma = 0) {
     const int FPW = 32 / Q;
-    return 32 * 33 + FPW;   // region stride = 2112 + 2*FPW floats: the filterbank phase reads 2 bins x FPW frames per lane
+    // region stride = 2112 + 2*FPW floats: the CUDA-core filterbank phase reads 2 bins x FPW frames per lane.
+    // Tensor-core filterbank: stride = 2112 + 4*FPW floats, so that the A-fragment loads (8 frame rows x 4 bins
+    // per instruction, kb_mma_a_off) hit 32 distinct banks for every Q.
+    return 32 * 33 + (fbmma ? 2 * FPW : FPW);
 }
 
 // Shared-memory carve-up; used by the host launcher (size) and by the kernel (offsets).
 KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_warps, int mode,
-                                     int n_bands, int n_chunks) {
+                                     int n_bands, int n_chunks, int fbmma = 0) {
     KbStftSmem s;
     const int P = 32 * Q;
     const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
@@ -53,7 +56,7 @@ KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_wa
     s.twp = off; off += kb_align16(Q * 33 * 8);
     s.twn = off; off += kb_align16((P / 2) * 8);
     s.cwq = off; off += Q * 16;
-    s.cw = off; if (fb) off += n_chunks * 16;
+    s.cw = off; if (fb && !fbmma) off += n_chunks * 16;   // fbmma: n_chunks = number of k-steps, cm holds their descriptors
     s.cm = off; if (fb) off += kb_align16(n_chunks * 8);
     s.cg = off; if (fb) off += kb_align16(33 * 4);
     s.bar = off; off += 16;
@@ -62,7 +65,7 @@ KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_wa
     s.Mp = n_bands | 1;
     s.samples = off; off += kb_align16((s.span + 8) * 4);  // +4 front (alignment shift) +4 back (rounded copy)
     s.outs = off; if (fb) off += kb_align16(TF * s.Mp * 4);
-    s.exw = kb_exw(Q);
+    s.exw = kb_exw(Q, fbmma);
     s.ex = off;  off += kb_align16(n_warps * s.exw * 8);
     s.total = off;
     return s;
@@ -127,6 +130,27 @@ KB_D void kb_bar_wait(KbBar* bar, unsigned parity) {
         "bra KB_WAIT_%=;\n\t"
         "KB_DONE_%=:\n\t}"
         ::"r"(b), "r"(parity) : "memory");
+}
+#endif
+
+// ---- tensor-core filterbank primitives ------------------------------------------------------
+// A-fragment element (frame f, bin k) of the tile's magnitudes: region of warp f / FPW, [bin][frame-in-warp].
+template <int FPW>
+KB_HD int kb_mma_a_off(int f, int RS) { return (f / FPW) * RS + (f % FPW); }
+KB_HD float kb_tf32_trunc(float v) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+#else
+    uint32_t u; std::memcpy(&u, &v, 4); u &= 0xffffe000u; float r; std::memcpy(&r, &u, 4); return r;
+#endif
+}
+#if !defined(KB_HOST_EMU)
+// D += A (16x8, row) . B (8x8, col), TF32 inputs, fp32 accumulate (SASS: HMMA.1688.F32.TF32)
+KB_D void kb_mma_tf32(float* d, const float* a, float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
+                   "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 #endif
 
@@ -362,6 +386,151 @@ KB_FN void kb_col_dftq_store(KbThreadRegs& R, cpx* region, int g, int q, int zst
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Filterbank phase on the tensor pipe: out[frame][band] += mag[frame][bin] . fb[bin][band] as a
+// block-banded GEMM of mma.sync m16n8k8 tiles (frames x 8 bins) . (8 bins x 8 bands), fp32-grade through the
+// 3xTF32 split (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi; the lo parts are exact differences).  Replaces
+// tf.tensordot of kapre/time_frequency.py:544.  A warp walks the job slots w, w + NW, ... of
+// kb_make_fb_mma; B fragments come pre-split from global memory (one 16 B load per lane and k-step,
+// prefetched one step ahead), A fragments are read from the warps' exchange regions and split in registers.
+// ------------------------------------------------------------------------------------------
+template <int Q>
+KB_FN void kb_fb_mma_load_a(const float* __restrict__ exf, int RS, int FR, int mt, int lane, int k0, float* a) {
+    constexpr int FPW = 32 / Q;
+    const int g = lane >> 2, t = lane & 3;
+    const int f0 = 16 * mt + g, f1 = f0 + 8;
+    const float* ap = exf + (k0 + t) * FPW;
+    if (f0 < FR) {
+        const float* r = ap + kb_mma_a_off<FPW>(f0, RS);
+        a[0] = r[0]; a[2] = r[4 * FPW];
+    } else { a[0] = 0.0f; a[2] = 0.0f; }
+    if (f1 < FR) {
+        const float* r = ap + kb_mma_a_off<FPW>(f1, RS);
+        a[1] = r[0]; a[3] = r[4 * FPW];
+    } else { a[1] = 0.0f; a[3] = 0.0f; }
+}
+
+// accumulator fragment -> out_s[frame][band] (added: a column tile may be split over two jobs)
+KB_FN void kb_fb_mma_flush(float* out_s, int Mp, int n_bands, int FR, int mt, int lane, int j, const float* acc) {
+    const int g = lane >> 2, t = lane & 3;
+    const int col = 8 * j + 2 * t;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int f = 16 * mt + g + 8 * h;
+        if (f < FR) {
+            float* o = out_s + f * Mp + col;
+#if defined(KB_HOST_EMU)
+            if (col < n_bands) o[0] += acc[2 * h];
+            if (col + 1 < n_bands) o[1] += acc[2 * h + 1];
+#else
+            if (col < n_bands) atomicAdd(o, acc[2 * h]);
+            if (col + 1 < n_bands) atomicAdd(o + 1, acc[2 * h + 1]);
+#endif
+        }
+    }
+}
+
+#if defined(KB_HOST_EMU)
+// Emulation of the whole phase: the fragments are gathered with the device code's per-lane addressing
+// (kb_fb_mma_load_a / the mw table / kb_fb_mma_flush) and multiplied as dense tiles per the PTX layouts
+// of mma.m16n8k8: A row g(+8) col t(+4); B row t(+4) col g; D row g(+8) cols 2t, 2t+1.
+template <int Q>
+inline void kb_fb_mma_phase(const float* exf, int RS, int FR, const kb_f4* mw, const kb_i2* ms_s, const int* mg_s,
+                            float* out_s, int Mp, int n_bands, int NW) {
+    const int MT = (FR + 15) >> 4;
+    for (int warp = 0; warp < NW; ++warp)
+        for (int slot = warp; slot < KB_MMA_SLOTS; slot += NW) {
+            std::vector<float> acc(2 * 32 * 4, 0.0f);
+            for (int i = mg_s[slot]; i < mg_s[slot + 1]; ++i) {
+                const kb_i2 sd = ms_s[i];
+                for (int mt = 0; mt < MT; ++mt) {
+                    float Ah[16][8], Al[16][8], Bh[8][8], Bl[8][8];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3;
+                        float a[4];
+                        kb_fb_mma_load_a<Q>(exf, RS, FR, mt, lane, sd.x, a);
+                        const int rr[4] = {g, g + 8, g, g + 8}, cc[4] = {t, t, t + 4, t + 4};
+                        for (int e = 0; e < 4; ++e) {
+                            const float hi = kb_tf32_trunc(a[e]);
+                            Ah[rr[e]][cc[e]] = hi;
+                            Al[rr[e]][cc[e]] = kb_tf32_trunc(a[e] - hi);
+                        }
+                        const kb_f4 b = mw[(size_t)i * 32 + lane];
+                        Bh[t][g] = b.x; Bh[t + 4][g] = b.y;
+                        Bl[t][g] = kb_tf32_trunc(b.z); Bl[t + 4][g] = kb_tf32_trunc(b.w);
+                    }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3;
+                        for (int e = 0; e < 4; ++e) {
+                            const int r = g + 8 * (e >> 1), c = 2 * t + (e & 1);
+                            float d = acc[(mt * 32 + lane) * 4 + e];
+                            float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+                            for (int k = 0; k < 8; ++k) { s1 += Al[r][k] * Bh[k][c]; s2 += Ah[r][k] * Bl[k][c]; s3 += Ah[r][k] * Bh[k][c]; }
+                            d += s1; d += s2; d += s3;
+                            acc[(mt * 32 + lane) * 4 + e] = d;
+                        }
+                    }
+                }
+                if (sd.y >= 0) {
+                    for (int mt = 0; mt < MT; ++mt)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            kb_fb_mma_flush(out_s, Mp, n_bands, FR, mt, lane, sd.y, &acc[(mt * 32 + lane) * 4]);
+                            for (int e = 0; e < 4; ++e) acc[(mt * 32 + lane) * 4 + e] = 0.0f;
+                        }
+                }
+            }
+        }
+}
+#else
+template <int Q>
+__device__ __forceinline__ void kb_fb_mma_phase(const float* __restrict__ exf, int RS, int FR,
+                                                const kb_f4* __restrict__ mw, const kb_i2* __restrict__ ms_s,
+                                                const int* __restrict__ mg_s, float* out_s, int Mp, int n_bands,
+                                                int NW) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MT = (FR + 15) >> 4;
+    for (int slot = warp; slot < KB_MMA_SLOTS; slot += NW) {
+        int i = mg_s[slot];
+        const int e = mg_s[slot + 1];
+        if (i >= e) continue;
+        float acc[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[mt][q] = 0.0f;
+        const float4* __restrict__ mw4 = reinterpret_cast<const float4*>(mw);
+        float4 bn = __ldg(mw4 + (size_t)i * 32 + lane);
+        for (; i < e; ++i) {
+            const kb_i2 sd = ms_s[i];
+            const float4 b = bn;
+            if (i + 1 < e) bn = __ldg(mw4 + (size_t)(i + 1) * 32 + lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                if (mt < MT) {
+                    float a[4], ah[4], al[4];
+                    kb_fb_mma_load_a<Q>(exf, RS, FR, mt, lane, sd.x, a);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { ah[q] = kb_tf32_trunc(a[q]); al[q] = a[q] - ah[q]; }
+                    kb_mma_tf32(acc[mt], al, b.x, b.y);
+                    kb_mma_tf32(acc[mt], ah, b.z, b.w);
+                    kb_mma_tf32(acc[mt], ah, b.x, b.y);
+                }
+            }
+            if (sd.y >= 0) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    if (mt < MT) {
+                        kb_fb_mma_flush(out_s, Mp, n_bands, FR, mt, lane, sd.y, acc[mt]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[mt][q] = 0.0f;
+                    }
+                }
+            }
+        }
+    }
+}
+#endif
+
 // One CTA's share of the work: tiles cta, cta + n_cta, ...
 template <int Q, int MODE>
 #if defined(KB_HOST_EMU)
@@ -380,7 +549,9 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     const int kb_nt = NW * 32;
     (void)kb_nt;
     const int H = p.hop, N = p.n_fft, TF = p.TF;
-    const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, p.n_chunks);
+    const bool fbmma = fbmode && p.fb_mma != 0;      // filterbank phase on the tensor pipe (kb_fb_mma_phase)
+    const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, fbmma ? p.n_msteps : p.n_chunks,
+                                             fbmma ? 1 : 0);
     float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
     cpx* __restrict__ twp_s = reinterpret_cast<cpx*>(smem + L.twp);
     cpx* __restrict__ twn_s = reinterpret_cast<cpx*>(smem + L.twn);
@@ -413,12 +584,23 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         for (int i = tid; i < Q * 33; i += kb_nt) { float2 t = p.twp[i]; twp_s[i] = cmake(t.x, t.y); }
         for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
         if (p.cosw) { for (int i = tid; i < Q; i += kb_nt) cwq_s[i] = p.cwq[i]; }
-        if (fbmode) {
+        if (fbmma) {
+            for (int i = tid; i < p.n_msteps; i += kb_nt) cm_s[i] = p.ms[i];
+            for (int i = tid; i <= KB_MMA_SLOTS; i += kb_nt) cg_s[i] = p.mg[i];
+            for (int i = tid; i < TF * L.Mp; i += kb_nt) out_s[i] = 0.0f;   // the phase accumulates into a zeroed tile
+        } else if (fbmode) {
             for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
             for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.cg[i];
         }
     KB_PHASE_END
     KB_SYNC_CTA;
+#if !defined(KB_HOST_EMU)
+    // Programmatic dependent launch: everything above only touched the plan's constant tables, so it
+    // overlaps the tail of the previous kernel in the stream; data (waveform, output, item maxima)
+    // is touched only after the predecessor has completed.  No-op without the launch attribute.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     unsigned par = 0;   // mbarrier phase parity (uniform across the CTA)
     if (cta < n_tiles) {
         const KbTilePlan tp = kb_plan_tile(p, span, cta);
@@ -438,6 +620,12 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         const float* __restrict__ smp_s = smp0 + tp.shift;
         const bool has_next = (tile + n_cta) < n_tiles;
 
+        if (fbmode && tile != cta && p.bulk_ok && !tp.bulk) {   // deferred cooperative load (see the prefetch above)
+            KB_PHASE_BEGIN
+                (void)R;
+                kb_issue_tile_loads(p, tp, smp0, span, bar, tid, kb_nt);
+            KB_PHASE_END
+        }
         // ---- wait for this tile's samples -----------------------------------------------------
         if (tp.bulk) {
 #if !defined(KB_HOST_EMU)
@@ -600,9 +788,9 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                         for (int gg = 0; gg < FPW; ++gg) mid[gg] = magr[(gg * (Q / 2 + 1) + Q / 2) * 2 + 0];
                         kb_store_vec<FPW>(mw + (P / 2) * FPW, mid);
                     }
-                    if (lane < 3) {
+                    if (lane < (fbmma ? 7 : 3)) {   // pad bins: chunks of 4 bins / k-steps of 8 bins read past bin P
 #pragma unroll
-                        for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;   // pad bins
+                        for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;
                     }
                 KB_PHASE_END
             }
@@ -611,16 +799,34 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         if (fbmode) {
             KB_SYNC_CTA;   // all magnitudes visible; sample buffer and out_s are free
             if (has_next) {
-                const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
-                KB_PHASE_BEGIN
-                    (void)R;
-                    if (tid == 0) *plan_s = tn;
-                    kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
-                KB_PHASE_END
+                if (p.bulk_ok) {
+                    // Warp 0 alone plans the next tile and issues its bulk copy (+ the zero fill of pad regions);
+                    // the other warps go straight to the filterbank.  A tile the bulk copy cannot serve (tensor
+                    // edge, all padding) is loaded cooperatively at the top of its own iteration.
+                    KB_PHASE_BEGIN
+                        (void)R;
+                        if (tid < 32) {
+                            const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
+                            if (tid == 0) *plan_s = tn;
+                            if (tn.bulk) kb_issue_tile_loads(p, tn, smp0, span, bar, tid, 32);
+                        }
+                    KB_PHASE_END
+                } else {
+                    const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
+                    KB_PHASE_BEGIN
+                        (void)R;
+                        if (tid == 0) *plan_s = tn;
+                        kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
+                    KB_PHASE_END
+                }
             }
             // ---- phase 5: filterbank ------------------------------------------------------------
             // 32 lane groups of NW lanes; lane w of a group owns the FPW frame columns held in warp
             // w's exchange region (one vector load per bin), the group walks its list of 4-bin chunks.
+            if (fbmma) {
+                kb_fb_mma_phase<Q>(reinterpret_cast<const float*>(ex_s), 2 * EXS, FR, p.mw, cm_s, cg_s, out_s, L.Mp,
+                                   p.n_bands, NW);
+            } else {
             KB_PHASE_BEGIN
                 (void)R;
                 const int warp = tid >> 5, lane = tid & 31;
@@ -656,6 +862,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                     }
                 }
             KB_PHASE_END
+            }
             KB_SYNC_CTA;
             // ---- phase 6: decibel + coalesced copy-out of the (TF x n_bands) block ----------
             KB_PHASE_BEGIN
@@ -668,8 +875,11 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 float rmax = R.runmax;
                 for (int colm = warp; colm < TF; colm += NW) {
                     const int t = t0 + colm;
-                    if (t >= p.T) break;
-                    const float* __restrict__ srow = out_s + colm * L.Mp;
+                    float* srow = out_s + colm * L.Mp;
+                    if (t >= p.T) {                  // frames past the end of the signal: nothing to write
+                        if (fbmma) { for (int m = lane; m < M; m += 32) srow[m] = 0.0f; }
+                        continue;
+                    }
                     if (sk == 1) {
                         // contiguous rows: four values per lane and trip, immediate offsets
                         float* __restrict__ orow = o + (long long)t * p.o_st;
@@ -678,6 +888,10 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                             float v[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) v[u] = srow[m + 32 * u];
+                            if (fbmma) {             // the tensor-core phase accumulates into a zeroed tile
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) srow[m + 32 * u] = 0.0f;
+                            }
                             if (dbmode) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
@@ -691,6 +905,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                         }
                         for (; m < M; m += 32) {
                             float v = srow[m];
+                            if (fbmma) srow[m] = 0.0f;
                             if (dbmode) {
                                 v = fmaxf(v, amin);
                                 rmax = fmaxf(rmax, v);
@@ -703,6 +918,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                         const int step = 32 * sk;
                         for (int m = lane; m < M; m += 32) {
                             float v = srow[m];
+                            if (fbmma) srow[m] = 0.0f;
                             if (dbmode) {
                                 v = fmaxf(v, amin);
                                 rmax = fmaxf(rmax, v);

@@ -15,7 +15,9 @@
 
 template <int Q, int MODE>
 static void run_stft_qm(const KbStftParams& p, int n_cta) {
-    const KbStftSmem L = kb_stft_smem_layout(Q, p.n_fft, p.hop, p.TF, p.n_warps, p.mode, p.n_bands, p.n_chunks);
+    const bool fbm = (p.mode == KB_OUT_FB || p.mode == KB_OUT_FB_DB) && p.fb_mma;
+    const KbStftSmem L = kb_stft_smem_layout(Q, p.n_fft, p.hop, p.TF, p.n_warps, p.mode, p.n_bands,
+                                             fbm ? p.n_msteps : p.n_chunks, fbm ? 1 : 0);
     std::vector<char> raw(L.total + 64 + 16);
     char* smem = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
     for (int cta = 0; cta < n_cta; ++cta) {
@@ -88,7 +90,7 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
                 int mode, void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk,
                 const float* fb, int n_freq, int n_bands, float amin, float db_mul, float db_sub,
                 unsigned int* item_max, int TF, int n_warps, int n_cta, int dbuf, int bulk, long long x_numel,
-                int db_on, long long ph_off) {
+                int db_on, long long ph_off, int fb_mma) {
     const int Q = kb_q_for_nfft(n_fft);
     if (!Q) return -1;
     if ((mode == KB_OUT_FB || mode == KB_OUT_FB_DB) && TF != n_warps * (32 / Q)) return -2;  // kernel contract
@@ -118,6 +120,11 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     p.bands = fb ? bands.data() : nullptr; p.fbw = fb ? fbw.data() : nullptr; p.n_bands = fb ? n_bands : 0;
     p.n_fbw = fb ? (int)fbw.size() : 0;
     if (fb) { p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
+    std::vector<kb_f4> mw; std::vector<kb_i2> ms; std::vector<int> mg;
+    if (fb && fb_mma) {
+        kb_make_fb_mma(fb, n_freq, n_bands, mw, ms, mg);
+        p.fb_mma = 1; p.mw = mw.data(); p.ms = ms.data(); p.mg = mg.data(); p.n_msteps = (int)ms.size();
+    }
     p.x_lo = x; p.x_hi = x + x_numel; p.x_numel = x_numel; p.x_align = (unsigned)(((uintptr_t)x >> 2) & 3);
     p.bulk_ok = (bulk && x_sl == 1) ? 1 : 0; p.dbuf = dbuf;
     p.amin = amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = item_max; p.db_on = db_on; p.ph_off = ph_off;

@@ -38,7 +38,7 @@ def _fp(a):
 
 
 def emu_stft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, out_fmt,
-             fb=None, amin=1e-5, ref=1.0, TF=16, n_warps=4, n_cta=3, dbuf=1, bulk=1, db_on=0):
+             fb=None, amin=1e-5, ref=1.0, TF=16, n_warps=4, n_cta=3, dbuf=1, bulk=1, db_on=0, fb_mma=0):
     """x: (B, L, C) channels_last or (B, C, L) channels_first float32.  Returns (out, item_max)."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -74,7 +74,7 @@ def emu_stft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt
                          _fp(window), mode, _fp(out), LL(osb), LL(osc), LL(ost), LL(osk),
                          fbp, nfreq, nb, ctypes.c_float(amin), ctypes.c_float(db_mul),
                          ctypes.c_float(db_sub), _fp(item_max), TF, n_warps, n_cta, dbuf, bulk, LL(x.size),
-                         db_on, LL(C * osc))
+                         db_on, LL(C * osc), int(fb_mma))
     assert rc == 0
     return out, item_max.view(np.float32)
 

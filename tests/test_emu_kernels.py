@@ -74,6 +74,42 @@ def test_emu_mel_and_db(n_fft, hop, n_mels, sr, TF, nw, fmt):
     np.testing.assert_allclose(imax2, lin.reshape(B, -1).max(1), rtol=1e-6)
 
 
+@pytest.mark.parametrize('n_fft,hop,n_mels,sr,TF,nw', [(1024, 256, 128, 22050, 16, 8), (1024, 256, 128, 22050, 8, 4),
+                                                        (512, 256, 40, 22050, 16, 4), (512, 128, 64, 16000, 32, 8),
+                                                        (2048, 512, 128, 44100, 8, 8), (2048, 512, 64, 44100, 16, 16),
+                                                        (256, 64, 20, 16000, 32, 4), (1024, 256, 77, 16000, 4, 2)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_emu_mel_tensor_core_filterbank(n_fft, hop, n_mels, sr, TF, nw, fmt):
+    """Filterbank phase as the block-banded mma.sync 3xTF32 GEMM (kb_fb_mma_phase): same tolerances as the
+    CUDA-core phase, incl. a band count that is no multiple of 8 and a half-filled 16-row tile (n_fft 2048, 8 warps)."""
+    rng = np.random.default_rng(n_mels + 1)
+    B = 2
+    x = wave(rng, B, 2, 6001, fmt)
+    x[1] *= 1e-3
+    w = O.get_window(None, n_fft).astype(np.float32)
+    fb = O.filterbank_mel(sr, n_fft // 2 + 1, n_mels, 0.0, None, False, 'slaney')
+    kw = dict(n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels, input_data_format=fmt, output_data_format=fmt)
+    ref = O.melspectrogram_layer(x, **kw)
+    out, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw, fb_mma=1)
+    assert nerr(out, ref) < 1e-6
+    refdb = O.melspectrogram_layer(x, return_decibel=True, db_dynamic_range=1e9, **kw)
+    outdb, imax = E.emu_stft(x, n_fft, n_fft, hop, w, True, True, E.MODE_FB_DB, fmt, fmt, fb=fb, TF=TF, n_warps=nw,
+                             fb_mma=1)
+    refdb2 = O.melspectrogram_layer(x, return_decibel=True, db_dynamic_range=1e9, pad_begin=True, pad_end=True, **kw)
+    assert np.abs(outdb - refdb2).max() < 5e-5
+
+
+def test_emu_log_filterbank_tensor_core():
+    rng = np.random.default_rng(10)
+    x = wave(rng, 1, 1, 4000, 'channels_first')
+    fb = O.filterbank_log(22050, 513, 84, 12)
+    ref = O.apply_filterbank(np.abs(O.stft_layer(x, 1024, None, 256, input_data_format='channels_first',
+                                                 output_data_format='channels_first')), fb.astype(np.float64), 'channels_first')
+    out, _ = E.emu_stft(x, 1024, 1024, 256, O.get_window(None, 1024), False, False, E.MODE_FB, 'channels_first',
+                        'channels_first', fb=fb, TF=16, n_warps=8, fb_mma=1)
+    assert nerr(out, ref) < 1e-6
+
+
 def test_emu_log_filterbank_dense_bands():
     rng = np.random.default_rng(9)
     x = wave(rng, 1, 1, 4000, 'channels_first')

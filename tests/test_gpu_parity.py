@@ -121,13 +121,17 @@ def test_stft_short_window_golden(K, golden, pad_end):
 @pytest.mark.parametrize('n_fft,hop,n_mels,sr', [(512, 256, 64, 16000), (1024, 256, 128, 22050), (2048, 512, 128, 44100),
                                                   (256, 128, 20, 8000), (1024, 160, 80, 16000)])
 @pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
-def test_melspectrogram_fused_vs_oracle(K, n_fft, hop, n_mels, sr, fmt):
+@pytest.mark.parametrize('fbmma', ['0', '1'])   # filterbank phase on the CUDA cores / as the mma.sync 3xTF32 GEMM
+def test_melspectrogram_fused_vs_oracle(K, monkeypatch, n_fft, hop, n_mels, sr, fmt, fbmma):
+    monkeypatch.setenv('KAPRE_B200_FBMMA', fbmma)
     rng = np.random.default_rng(n_fft)
     x = wave(rng, 3, 2, 9000, fmt)
     x[1] *= 1e-3  # a quiet item: the per-item maximum must not leak between items
     kw = dict(n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels, input_data_format=fmt, output_data_format=fmt)
     xt = torch.from_numpy(x).cuda()
     mel = K.get_melspectrogram_layer(**kw)(xt).cpu().numpy()
+    if fmt == 'channels_first':   # planar tensors run the single-channel tiles, which honour the switch
+        assert ('fbmma' + fbmma) in K._native.last_launch_info()
     ref = O.melspectrogram_layer(x, **kw)
     assert mel.shape == ref.shape
     assert nerr(mel, ref) < 2e-6
@@ -233,7 +237,9 @@ def test_apply_filterbank_standalone(K, fmt, kind):
     assert nerr(got, ref) < 2e-6
 
 
-def test_log_frequency_layer_fused(K):
+@pytest.mark.parametrize('fbmma', ['0', '1'])
+def test_log_frequency_layer_fused(K, monkeypatch, fbmma):
+    monkeypatch.setenv('KAPRE_B200_FBMMA', fbmma)
     rng = np.random.default_rng(12)
     x = wave(rng, 2, 1, 8000, 'channels_last')
     seq = K.get_log_frequency_spectrogram_layer(n_fft=1024, hop_length=256, return_decibel=True)
