@@ -159,6 +159,13 @@ const char* kapre_last_launch_info(void);
 int kapre_profile_enable(int enable);
 int kapre_profile_read(double* total_ms, uint64_t* launches);
 
+/* Experimental (measured prototype, not on the product path): stage 1 of the 32 x 32 factorisation of the
+ * n_fft = 1024 / hop = 256 real FFT as a tcgen05 (5th-gen tensor core) GEMM with TMEM accumulators, fp32-grade via
+ * the 3xTF32 split.  Layout of `out_dev` and the meaning of `store` are documented at the definition
+ * (kapre_b200/csrc/kapre_b200.cu) and in DESIGN.md. */
+int kapre_tc_dft_stage1(const float* x_dev, int n_items, long long item_stride, int length, float* out_dev, int store,
+                        int* grid_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

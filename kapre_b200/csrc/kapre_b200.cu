@@ -19,6 +19,7 @@
 #include "stft_mc_core.cuh"
 #include "istft_core.cuh"
 #include "aux_core.cuh"
+#include "tc_dft.cuh"
 
 // ------------------------------------------------------------------------------------------
 // error handling
@@ -78,6 +79,13 @@ template <int Q, int MODE>
 __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel(const __grid_constant__ KbStftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
     kb_stft_cta<Q, MODE>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// variant with the filterbank phase on the tensor pipe (mma.sync 3xTF32), selected by KAPRE_B200_FBMMA=1
+template <int Q, int MODE>
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel_mma(const __grid_constant__ KbStftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_stft_cta<Q, MODE, 1>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // 16-warp CTAs, one per SM: n_fft = 2048 in the filterbank modes, where an 8-warp CTA already needs more than
@@ -358,7 +366,7 @@ static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int m
     for (int a = 0; a < 4; ++a) {
         const int NW = nws[a];
         if (force_nw && NW != force_nw) continue;
-        if (NW == 16 && !(Q == 32 && fb)) continue;      // only kb_stft_kernel_w16's instantiations
+        if (NW == 16 && !(Q == 32 && fb && !fbmma)) continue;      // only kb_stft_kernel_w16's instantiations
         const int FR = NW * FPW;
         if (FR > 32) continue;
         for (int TF = 32; TF >= 1; TF >>= 1) {
@@ -420,6 +428,16 @@ static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStre
             return 0;
         } else {
             return kb_fail(KAPRE_E_UNSUPPORTED, "no 16-warp instantiation for Q=%d mode=%d", Q, MODE);
+        }
+    }
+    if constexpr (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB) {
+        if (p.fb_mma) {
+            int rc = kb_set_smem(kb_stft_kernel_mma<Q, MODE>, smem);
+            if (rc) return rc;
+            KbProfScope prof(st);
+            if ((rc = kb_launch_pdl(kb_stft_kernel_mma<Q, MODE>, grid, p.n_warps * 32, smem, st, p))) return rc;
+            g_launches++;
+            return 0;
         }
     }
     int rc = kb_set_smem(kb_stft_kernel<Q, MODE>, smem);
@@ -1176,6 +1194,56 @@ int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_ite
     g_launches++;
     return kb_launch_clamp(out_dev, n_items, item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
                            db->dynamic_range, st);
+}
+
+// ---- experimental: tensor-core (tcgen05) DFT stage, see tc_dft.cuh -----------------------------------
+// Stage 1 of the 32 x 32 factorisation of the n_fft = 1024 / hop = 256 real FFT over `n_items` waveforms of
+// `length` samples (`item_stride` floats apart).  store != 0: out = (items, T, 32, 32) floats with
+// out[i, f, n2, 2 k1 + {0,1}] = Re / Im of sum_n1 x[256 f + 32 n1 + n2] exp(-2 pi i n1 k1 / 32), k1 = 0..15, except
+// column 1 (Im of k1 = 0, identically zero), which carries the real k1 = 16 sum.  store == 0 (timing): out must
+// hold grid * 256 floats of checksums; *grid_out receives the grid size.  T = 1 + (length - 1024) / 256.
+int kapre_tc_dft_stage1(const float* x_dev, int n_items, long long item_stride, int length, float* out_dev, int store,
+                        int* grid_out, void* stream) {
+    if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    if (n_items < 1 || length < KB_TC_NFFT) return kb_fail(KAPRE_E_INVALID, "need n_items >= 1 and length >= 1024");
+    DevInfo dev;
+    int rc = kb_dev_info(&dev);
+    if (rc) return rc;
+    static float* d_fmat[64] = {nullptr};
+    if (dev.device < 0 || dev.device >= 64) return kb_fail(KAPRE_E_UNSUPPORTED, "device index");
+    if (!d_fmat[dev.device]) {
+        std::vector<float> f(2048);
+        for (int kc = 0; kc < 8; ++kc)
+            for (int c = 0; c < 32; ++c)
+                for (int e = 0; e < 4; ++e) {
+                    const int n1 = 4 * kc + e, k1 = c >> 1;
+                    double v;
+                    if (c == 1) v = (n1 & 1) ? -1.0 : 1.0;                       // k1 = 16: (-1)^n1
+                    else {
+                        const double a = -2.0 * M_PI * (double)((n1 * k1) % 32) / 32.0;
+                        v = (c & 1) ? sin(a) : cos(a);
+                    }
+                    const float w = (float)v, hi = kb_tf32_hi(w);
+                    f[(size_t)(kc * 32 + c) * 4 + e] = hi;
+                    f[1024 + (size_t)(kc * 32 + c) * 4 + e] = w - hi;
+                }
+        if ((rc = kb_upload(f, &d_fmat[dev.device]))) return rc;
+    }
+    KbTcParams p{};
+    p.x = x_dev; p.item_stride = item_stride; p.n_items = n_items; p.length = length;
+    p.T = 1 + (length - KB_TC_NFFT) / KB_TC_HOP;
+    p.out = out_dev; p.store = store; p.fmat = d_fmat[dev.device];
+    p.n_tiles_t = (p.T + KB_TC_TILE_F - 1) / KB_TC_TILE_F;
+    const long long tiles = (long long)n_items * p.n_tiles_t;
+    const long long gmax = (long long)dev.sm_count * 2;
+    const int grid = (int)(tiles < gmax ? tiles : gmax);
+    if (grid_out) *grid_out = grid;
+    if ((rc = kb_set_smem(kb_tc_dft_stage1_kernel, KB_TC_SMEM))) return rc;
+    KbProfScope prof((cudaStream_t)stream);
+    kb_tc_dft_stage1_kernel<<<grid, KB_TC_THREADS, KB_TC_SMEM, (cudaStream_t)stream>>>(p);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
 }
 
 }  // extern "C"

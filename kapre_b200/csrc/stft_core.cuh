@@ -167,12 +167,11 @@ struct KbTilePlan {
     int bytes;           // multiple of 16
 };
 
-KB_HD KbTilePlan kb_plan_tile(const KbStftParams& p, int span, int tile) {
+// Plan of the tile `tt` (index along time) of signal `sig` = b * C + c.
+KB_HD KbTilePlan kb_plan_tile_at(const KbStftParams& p, int span, unsigned sig, int tt) {
     // Executed by every thread once or twice per tile, so it is kept to 32-bit arithmetic
     // except for the final pointer.
     KbTilePlan t;
-    const unsigned sig = (unsigned)tile / (unsigned)p.n_tiles_t;
-    const int tt = tile - (int)sig * p.n_tiles_t;
     if (p.C == 1) { t.b = (int)sig; t.c = 0; }
     else { t.b = (int)(sig / (unsigned)p.C); t.c = (int)sig - t.b * p.C; }
     t.t0 = tt * p.TF;
@@ -199,6 +198,11 @@ KB_HD KbTilePlan kb_plan_tile(const KbStftParams& p, int span, int tile) {
         }
     }
     return t;
+}
+
+KB_HD KbTilePlan kb_plan_tile(const KbStftParams& p, int span, int tile) {
+    const unsigned sig = (unsigned)tile / (unsigned)p.n_tiles_t;
+    return kb_plan_tile_at(p, span, sig, tile - (int)sig * p.n_tiles_t);
 }
 
 // Issue the loads of one tile into sample buffer `buf` (all threads call this).
@@ -532,7 +536,7 @@ __device__ __forceinline__ void kb_fb_mma_phase(const float* __restrict__ exf, i
 #endif
 
 // One CTA's share of the work: tiles cta, cta + n_cta, ...
-template <int Q, int MODE>
+template <int Q, int MODE, int FBMMA = 0>
 #if defined(KB_HOST_EMU)
 inline void kb_stft_cta(const KbStftParams& p, char* smem, int cta, int n_cta)
 #else
@@ -549,7 +553,9 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     const int kb_nt = NW * 32;
     (void)kb_nt;
     const int H = p.hop, N = p.n_fft, TF = p.TF;
-    const bool fbmma = fbmode && p.fb_mma != 0;      // filterbank phase on the tensor pipe (kb_fb_mma_phase)
+    // filterbank phase on the tensor pipe (kb_fb_mma_phase): a separate instantiation, measured slower than the
+    // CUDA-core chunk lists (profiles/r2_fbmma_ab.md), kept selectable for the A/B
+    constexpr bool fbmma = fbmode && FBMMA != 0;
     const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, fbmma ? p.n_msteps : p.n_chunks,
                                              fbmma ? 1 : 0);
     float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
@@ -610,6 +616,11 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         KB_PHASE_END
     }
 
+    // filterbank modes step (signal, tile-in-signal) by n_cta tiles per iteration
+    const unsigned step_sig = (unsigned)n_cta / (unsigned)p.n_tiles_t;
+    const int step_tt = n_cta - (int)step_sig * p.n_tiles_t;
+    unsigned nx_sig = (unsigned)cta / (unsigned)p.n_tiles_t;
+    int nx_tt = cta - (int)nx_sig * p.n_tiles_t;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
         // filterbank modes: the plan was computed once when the tile's loads were issued and parked
         // in shared memory (a CTA barrier lies in between); otherwise recompute it (cheap per frame
@@ -620,12 +631,6 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         const float* __restrict__ smp_s = smp0 + tp.shift;
         const bool has_next = (tile + n_cta) < n_tiles;
 
-        if (fbmode && tile != cta && p.bulk_ok && !tp.bulk) {   // deferred cooperative load (see the prefetch above)
-            KB_PHASE_BEGIN
-                (void)R;
-                kb_issue_tile_loads(p, tp, smp0, span, bar, tid, kb_nt);
-            KB_PHASE_END
-        }
         // ---- wait for this tile's samples -----------------------------------------------------
         if (tp.bulk) {
 #if !defined(KB_HOST_EMU)
@@ -799,26 +804,15 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         if (fbmode) {
             KB_SYNC_CTA;   // all magnitudes visible; sample buffer and out_s are free
             if (has_next) {
-                if (p.bulk_ok) {
-                    // Warp 0 alone plans the next tile and issues its bulk copy (+ the zero fill of pad regions);
-                    // the other warps go straight to the filterbank.  A tile the bulk copy cannot serve (tensor
-                    // edge, all padding) is loaded cooperatively at the top of its own iteration.
-                    KB_PHASE_BEGIN
-                        (void)R;
-                        if (tid < 32) {
-                            const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
-                            if (tid == 0) *plan_s = tn;
-                            if (tn.bulk) kb_issue_tile_loads(p, tn, smp0, span, bar, tid, 32);
-                        }
-                    KB_PHASE_END
-                } else {
-                    const KbTilePlan tn = kb_plan_tile(p, span, tile + n_cta);
-                    KB_PHASE_BEGIN
-                        (void)R;
-                        if (tid == 0) *plan_s = tn;
-                        kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
-                    KB_PHASE_END
-                }
+                // (signal, tile-in-signal) of the next tile, stepped without a division
+                nx_sig += step_sig; nx_tt += step_tt;
+                if (nx_tt >= p.n_tiles_t) { nx_tt -= p.n_tiles_t; ++nx_sig; }
+                const KbTilePlan tn = kb_plan_tile_at(p, span, nx_sig, nx_tt);
+                KB_PHASE_BEGIN
+                    (void)R;
+                    if (tid == 0) *plan_s = tn;
+                    kb_issue_tile_loads(p, tn, smp0, span, bar, tid, kb_nt);
+                KB_PHASE_END
             }
             // ---- phase 5: filterbank ------------------------------------------------------------
             // 32 lane groups of NW lanes; lane w of a group owns the FPW frame columns held in warp

@@ -20,7 +20,7 @@ __all__ = [
     'hz_to_mel', 'mel_to_hz', 'filterbank_mel', 'filterbank_log', 'apply_filterbank',
     'magnitude_to_decibel', 'inverse_stft_window', 'inverse_stft_frames', 'istft_layer',
     'melspectrogram_layer', 'stft_magnitude_layer', 'phase', 'stft_mag_phase_layer',
-    'delta', 'frame_layer', 'energy_layer', 'logmel_to_mfcc',
+    'delta', 'frame_layer', 'energy_layer', 'logmel_to_mfcc', 'dft_stage1_32x32',
 ]
 
 CH_FIRST = 'channels_first'
@@ -467,3 +467,17 @@ def logmel_to_mfcc(x, n_mfccs=20, data_format='default'):
     if df == CH_LAST:
         y = np.transpose(y, (0, 1, 3, 2))
     return y
+
+
+def dft_stage1_32x32(x, n_fft=1024, hop=256):
+    """First stage of the 32 x 32 Cooley-Tukey split of the real FFT inside ``tf.signal.stft``
+    (kapre/time_frequency.py:174-182), float64: S[i, f, n2, k1] = sum_n1 x[i, hop f + 32 n1 + n2] exp(-2 pi i n1 k1 / 32),
+    k1 = 0..16.  Checker for the tensor-core prototype (kapre_b200/csrc/tc_dft.cuh); window-free by design."""
+    x = np.asarray(x, dtype=np.float64)
+    T = 1 + (x.shape[1] - n_fft) // hop
+    idx = hop * np.arange(T)[:, None] + np.arange(n_fft)[None, :]
+    fr = x[:, idx].reshape(x.shape[0], T, 32, 32)            # (i, f, n1, n2)
+    n1 = np.arange(32)[:, None]
+    k1 = np.arange(17)[None, :]
+    F = np.exp(-2j * np.pi * n1 * k1 / 32.0)                  # (n1, k1)
+    return np.einsum('ifab,ak->ifbk', fr, F)                  # (i, f, n2, k1)

@@ -22,6 +22,9 @@ static void run_stft_qm(const KbStftParams& p, int n_cta) {
     char* smem = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
     for (int cta = 0; cta < n_cta; ++cta) {
         std::fill(raw.begin(), raw.end(), (char)0x7f);  // poison: catches reads of unwritten smem
+        if constexpr (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB) {
+            if (fbm) { kb_stft_cta<Q, MODE, 1>(p, smem, cta, n_cta); continue; }
+        }
         kb_stft_cta<Q, MODE>(p, smem, cta, n_cta);
     }
 }
