@@ -32,9 +32,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CFG = dict(batch=256, length=110250, channels=1, sample_rate=22050, n_fft=1024, hop=256, n_mels=128)
-WORKLOAD = ('cfg2: batch=256 mono 22.05kHz 5s, n_fft=1024 hop=256 n_mels=128, '
-            'get_melspectrogram_layer(return_decibel=True), channels_last')
+# BASELINE.json configs[1] (the configuration the metric is quoted on; every rank runs one such batch: weak scaling)
+# and configs[4] (batch 8192 x 10 s sharded over the ranks with kapre_b200.sharding.shard_range: 1024 items per
+# rank on 8 GPUs).  Default: cfg2 below 8 ranks, cfg5 on 8.
+CONFIGS = {
+    'cfg2': dict(batch=256, sharded=False, length=110250, channels=1, sample_rate=22050, n_fft=1024, hop=256, n_mels=128,
+                 workload='cfg2: batch=256 mono 22.05kHz 5s, n_fft=1024 hop=256 n_mels=128, '
+                          'get_melspectrogram_layer(return_decibel=True), channels_last'),
+    'cfg5': dict(batch=8192, sharded=True, length=160000, channels=1, sample_rate=16000, n_fft=1024, hop=256, n_mels=128,
+                 workload='cfg5: batch=8192 mono 16kHz 10s log-mel, n_fft=1024 hop=256 n_mels=128, sharded over the ranks, '
+                          'get_melspectrogram_layer(return_decibel=True), channels_last'),
+}
+CFG = dict(CONFIGS['cfg2'])
+WORKLOAD = CFG['workload']
+
+
+def select_config(name, rank, world):
+    """Set the module-level CFG to this rank's share of the named configuration."""
+    global CFG, WORKLOAD
+    from kapre_b200.sharding import shard_range
+    CFG = dict(CONFIGS[name])
+    CFG['name'] = name
+    CFG['global_batch'] = CFG['batch'] if CFG['sharded'] else CFG['batch'] * world
+    if CFG['sharded']:
+        lo, hi = shard_range(CFG['batch'], rank, world)
+        CFG['batch'] = hi - lo
+        CFG['shard'] = [lo, hi]
+    WORKLOAD = CFG['workload']
 PROFILE_EVERY = 8  # every 8th fused-kernel launch of the timed loop is bracketed by CUDA events (roofline.kernel_ms)
 N_SETS = 3  # rotating input/output sets: 3 x (113 MB in + 56 MB out) = 507 MB > 126 MB L2
 
@@ -156,10 +180,10 @@ def run_cpu(steps, warmup, budget_s):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return dict(value=frames_per_step() * done / dt, unit='frames/s', cores=torch.get_num_threads(), kind='port',
+    return dict(value=frames_per_step() * done / dt, unit='frames/s', cores=torch.get_num_threads(), host_cores=cores, kind='port',
                 steps_timed=done,
-                sample='%d passes over the cfg2 batch (%d frames each), torch-CPU fp32 op-by-op port of the '
-                       'reference graph, best of {8,16,32,64,all=%d} threads, %.1f s' % (done, frames_per_step(), cores, dt)), dt / done
+                sample='%d passes over a %d-item batch of %s (%d frames each), torch-CPU fp32 op-by-op port of the '
+                       'reference graph, best of {8,16,32,64,all=%d} threads, %.1f s' % (done, CFG['batch'], CFG.get('name', 'cfg2'), frames_per_step(), cores, dt)), dt / done
 
 
 def main():
@@ -169,6 +193,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--config', default='auto', choices=['auto', 'cfg2', 'cfg5'],
+                    help='auto: cfg2 per rank below 8 ranks (weak scaling), cfg5 (batch 8192 sharded) on 8 ranks')
+    ap.add_argument('--no-numa-bind', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -178,11 +205,14 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
+        select_config(('cfg5' if world >= 8 else 'cfg2') if args.config == 'auto' else args.config, 0, max(world, 1))
+        if CFG['batch'] > 512:                            # bounded sample of this arm's workload: a 512-item slice per pass
+            CFG['batch'] = 512
         base, s_per_step = run_cpu(args.steps, warmup, budget_s=150.0)
         line = {'impl': 'reference', 'metric': 'mel_frames_per_sec', 'value': base['value'], 'unit': 'frames/s',
                 'n_gpus': args.gpus, 'steps': base['steps_timed'], 'warmup': warmup, 'ms_per_step': s_per_step * 1e3,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                'data': 'synthetic U(-1,1) waveforms', 'config': {'workload': WORKLOAD, 'device': 'host CPU'},
+                'data': 'synthetic U(-1,1) waveforms', 'config': {'workload': WORKLOAD, 'name': CFG['name'], 'device': 'host CPU', 'items_per_pass': CFG['batch']},
                 'cpu_baseline': base,
                 'e2e': {'value': base['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0,
@@ -198,6 +228,10 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    select_config(('cfg5' if world >= 8 else 'cfg2') if args.config == 'auto' else args.config, rank, world)
+    # host side of the end-to-end path: this rank's CPU threads and page-locked pools on the GPU's NUMA node
+    from kapre_b200 import hostmem
+    numa = {'node': None} if args.no_numa_bind else hostmem.bind_to_gpu_node(local_rank)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) with
         # C stdio to fd 1, so fd 1 points at stderr while the communicator is created
@@ -228,12 +262,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from kapre_b200.sharding import reduce_max as _reduce_max
+
     def reduce_max(v):
+        return _reduce_max(v, device=dev)
+
+    def reduce_sum(v):
         if world > 1:
-            t = torch.tensor([v], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
             return float(t.item())
-        return v
+        return float(v)
 
     # ---------------- end to end through predict() with pinned host buffers ---------------------
     def run_e2e():
@@ -286,11 +325,12 @@ def main():
     launches = _native.launch_count() - n0
     kern_ms, kern_n = _native.profile_read()
     ms_per_step = ms_total / args.steps
-    value = world * frames * args.steps / (ms_total * 1e-3)
+    frames_all = reduce_sum(frames)                       # all ranks' frames per step (shards may differ by one item)
+    value = frames_all * args.steps / (ms_total * 1e-3)
 
     if not e2e_first:
         xh, y_host, e2e_steps, e2e_s = run_e2e()
-    e2e_value = world * frames * e2e_steps / e2e_s
+    e2e_value = frames_all * e2e_steps / e2e_s
     h2d = xh[0].numel() * 4
     d2h = int(y_host.size) * 4
     # PCIe ceiling of that call: the same two buffers copied concurrently on two streams, nothing else
@@ -310,7 +350,23 @@ def main():
         _copies()
     torch.cuda.synchronize()
     pcie_s = (time.perf_counter() - t0) / 5
-    pcie_bound = world * frames / pcie_s
+    pcie_bound = frames_all / pcie_s
+
+    # ---------------- the same call on PAGEABLE memory (what a kapre user passes: a plain NumPy array) ----------
+    pageable = None
+    try:
+        xn = xh[0].numpy().copy()                       # ordinary malloc'ed array, not page-locked
+        layer.predict(xn)
+        barrier()
+        t0 = time.perf_counter()
+        n_pg = 3
+        for _ in range(n_pg):
+            layer.predict(xn)
+        torch.cuda.synchronize()
+        pageable = frames_all * n_pg / reduce_max(time.perf_counter() - t0)
+        del xn
+    except Exception as e:  # noqa: BLE001  (a reported extra, never fatal for the bench line)
+        print('[bench] pageable predict failed: %r' % (e,), file=sys.stderr)
 
     # ---------------- parity spot check of what was timed ---------------------------------------
     import oracle
@@ -337,18 +393,21 @@ def main():
     traffic_file = os.path.join(ROOT, 'profiles', 'traffic_bytes_per_launch.json')
     if os.path.exists(traffic_file):
         try:
-            roofline['traffic'] = json.load(open(traffic_file)).get('cfg2_fb_db')
+            roofline['traffic'] = json.load(open(traffic_file)).get(CFG['name'] + '_fb_db')
         except Exception:
             pass
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is an N=1 measurement (rank 0 has the box to itself)
+        hostmem.restore_affinity(numa)                # the CPU arm gets every host core
         cpu, _ = run_cpu(steps=40, warmup=1, budget_s=12.0)
     line = {
         'metric': 'mel_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic U(-1,1) waveforms, generated on device (seeded)',
-        'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': frames, 'global_batch': CFG['batch'] * world,
-                   'parallelism': 'dp%d (batch sharded, no collective in the data path)' % world,
+        'config': {'workload': WORKLOAD, 'name': CFG['name'], 'frames_per_step_per_gpu': frames,
+                   'global_batch': CFG['global_batch'], 'items_per_gpu': CFG['batch'],
+                   'parallelism': 'dp%d (batch sharded with kapre_b200.sharding.shard_range, no collective in the data path)' % world,
+                   'numa': {'gpu_node': numa.get('node'), 'cpus_bound': numa.get('cpus')},
                    'l2': '%d rotating input/output sets (%.0f MB) > 126 MB L2' % (
                        N_SETS, N_SETS * algorithmic_bytes_per_step() / 1e6),
                    'launch': _native.last_launch_info(), 'host_submit_ms_per_step': host_submit_ms},
@@ -356,7 +415,8 @@ def main():
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'steps': e2e_steps, 'api': 'Sequential.predict(pinned host tensor) -> host array',
-                'pcie_bound': pcie_bound, 'frac_of_pcie_bound': e2e_value / pcie_bound},
+                'pcie_bound': pcie_bound, 'frac_of_pcie_bound': e2e_value / pcie_bound,
+                'pageable_numpy_input': pageable},
         'gpu_launches': launches,
         'clocks': sampler.summary(),
         'max_abs_err_db_vs_oracle': max_err_db,

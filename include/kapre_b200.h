@@ -164,7 +164,7 @@ int kapre_profile_read(double* total_ms, uint64_t* launches);
  * the 3xTF32 split.  Layout of `out_dev` and the meaning of `store` are documented at the definition
  * (kapre_b200/csrc/kapre_b200.cu) and in DESIGN.md. */
 int kapre_tc_dft_stage1(const float* x_dev, int n_items, long long item_stride, int length, float* out_dev, int store,
-                        int* grid_out, void* stream);
+                        int* grid_out, const float* fmat_override_dev, void* stream);
 
 #ifdef __cplusplus
 }

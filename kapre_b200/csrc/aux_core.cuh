@@ -19,30 +19,40 @@ struct KbFbParams {
     int n_bands;
     float* out;
     long long o_sb, o_sc, o_st, o_sk;
-    int n_tiles_t;                        // ceil(T / 32)
+    int n_tiles_t;                        // ceil(T / R)
     int n_warps;
+    int R;                                // frames per tile: 32, or 16 / 8 / 4 / 2 / 1 when 32 spectra do not fit shared memory
 };
 
+// A tile holds R whole spectra ([bin][frame], row stride R + 1); R shrinks for long spectra (n_fft 4096: 2049 bins
+// -> 16 frames) so that every n_freq the STFT kernels produce can be filtered.
 struct KbFbSmem { int mag, outs, total, Mp; };
-KB_HD KbFbSmem kb_fb_smem_layout(int F, int n_bands) {
+KB_HD KbFbSmem kb_fb_smem_layout(int F, int n_bands, int R = 32) {
     KbFbSmem s;
     s.Mp = n_bands | 1;
     s.mag = 0;
-    s.outs = kb_align16((F + 3) * 33 * 4);
-    s.total = s.outs + kb_align16(32 * s.Mp * 4);
+    s.outs = kb_align16((F + 3) * (R + 1) * 4);
+    s.total = s.outs + kb_align16(R * s.Mp * 4);
     return s;
 }
+static inline int kb_fb_pick_r(int F, int n_bands, int smem_limit) {
+    for (int R = 32; R >= 1; R >>= 1)
+        if (kb_fb_smem_layout(F, n_bands, R).total <= smem_limit) return R;
+    return 0;
+}
 
+template <int FRT>
 #if defined(KB_HOST_EMU)
-inline void kb_fb_cta(const KbFbParams& p, char* smem, int cta, int n_cta)
+inline void kb_fb_cta_r(const KbFbParams& p, char* smem, int cta, int n_cta)
 #else
-__device__ __forceinline__ void kb_fb_cta(const KbFbParams& p, char* smem, int cta, int n_cta)
+__device__ __forceinline__ void kb_fb_cta_r(const KbFbParams& p, char* smem, int cta, int n_cta)
 #endif
 {
+    constexpr int RS = FRT + 1;
     const int NW = p.n_warps;
     const int kb_nt = NW * 32;
     (void)kb_nt;
-    const KbFbSmem L = kb_fb_smem_layout(p.F, p.n_bands);
+    const KbFbSmem L = kb_fb_smem_layout(p.F, p.n_bands, FRT);
     float* mag_s = reinterpret_cast<float*>(smem + L.mag);
     float* out_s = reinterpret_cast<float*>(smem + L.outs);
     const int n_tiles = p.B * p.C * p.n_tiles_t;
@@ -55,35 +65,37 @@ __device__ __forceinline__ void kb_fb_cta(const KbFbParams& p, char* smem, int c
         const int sig = tile / p.n_tiles_t;
         const int tt = tile - sig * p.n_tiles_t;
         const int b = sig / p.C, c = sig - b * p.C;
-        const int t0 = tt * 32;
+        const int t0 = tt * FRT;
         const float* xs = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc;
         const long long obase = (long long)b * p.o_sb + (long long)c * p.o_sc;
         KB_PHASE_BEGIN
             (void)R;
-            const int tot = 32 * p.F;
-            for (int idx = tid; idx < 3 * 33; idx += kb_nt) mag_s[p.F * 33 + idx] = 0.0f;  // pad rows
+            const int tot = FRT * p.F;
+            for (int idx = tid; idx < 3 * RS; idx += kb_nt) mag_s[p.F * RS + idx] = 0.0f;  // pad rows
             for (int idx = tid; idx < tot; idx += kb_nt) {
                 const int r = idx / p.F, k = idx - r * p.F;
                 const int t = t0 + r;
-                mag_s[k * 33 + r] = (t < p.T) ? xs[(long long)t * p.x_st + (long long)k * p.x_sk] : 0.0f;
+                mag_s[k * RS + r] = (t < p.T) ? xs[(long long)t * p.x_st + (long long)k * p.x_sk] : 0.0f;
             }
         KB_PHASE_END
         KB_SYNC_CTA;
         KB_PHASE_BEGIN
             (void)R;
             const int warp = tid >> 5, lane = tid & 31;
-            const float* mcol = mag_s + lane;
-            for (int m = warp; m < p.n_bands; m += NW) {
-                const KbBand bd = p.bands[m];
-                const float acc = kb_band_dot<33>(p.fbw + bd.off, mcol + bd.lo * 33, (bd.hi - bd.lo) >> 2);
-                out_s[lane * L.Mp + m] = acc;
+            if (lane < FRT) {
+                const float* mcol = mag_s + lane;
+                for (int m = warp; m < p.n_bands; m += NW) {
+                    const KbBand bd = p.bands[m];
+                    const float acc = kb_band_dot<RS>(p.fbw + bd.off, mcol + bd.lo * RS, (bd.hi - bd.lo) >> 2);
+                    out_s[lane * L.Mp + m] = acc;
+                }
             }
         KB_PHASE_END
         KB_SYNC_CTA;
         KB_PHASE_BEGIN
             (void)R;
             const int M = p.n_bands;
-            const int tot = 32 * M;
+            const int tot = FRT * M;
             for (int idx = tid; idx < tot; idx += kb_nt) {
                 const int r = idx / M, m = idx - r * M;
                 const int t = t0 + r;
@@ -91,6 +103,22 @@ __device__ __forceinline__ void kb_fb_cta(const KbFbParams& p, char* smem, int c
             }
         KB_PHASE_END
         KB_SYNC_CTA;
+    }
+}
+
+#if defined(KB_HOST_EMU)
+inline void kb_fb_cta(const KbFbParams& p, char* smem, int cta, int n_cta)
+#else
+__device__ __forceinline__ void kb_fb_cta(const KbFbParams& p, char* smem, int cta, int n_cta)
+#endif
+{
+    switch (p.R) {
+        case 32: kb_fb_cta_r<32>(p, smem, cta, n_cta); break;
+        case 16: kb_fb_cta_r<16>(p, smem, cta, n_cta); break;
+        case 8: kb_fb_cta_r<8>(p, smem, cta, n_cta); break;
+        case 4: kb_fb_cta_r<4>(p, smem, cta, n_cta); break;
+        case 2: kb_fb_cta_r<2>(p, smem, cta, n_cta); break;
+        default: kb_fb_cta_r<1>(p, smem, cta, n_cta); break;
     }
 }
 

@@ -19,6 +19,7 @@
 #include "stft_mc_core.cuh"
 #include "istft_core.cuh"
 #include "aux_core.cuh"
+#include "mr_core.cuh"
 #include "tc_dft.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -126,6 +127,11 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_fb_kernel(const __grid_c
 __global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_dft_kernel(const __grid_constant__ KbDftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
     kb_dft_cta(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_mr_kernel(const __grid_constant__ KbMrParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_mr_cta(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
 __global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_idft_kernel(const __grid_constant__ KbIdftParams p) {
@@ -770,14 +776,47 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         p.win_eff = plan->win_eff; p.w = plan->w; p.tw = plan->tw;
         p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
         p.mode = mode; p.n_tiles_t = (T + KB_DFT_TF - 1) / KB_DFT_TF; p.n_warps = 8;
+        {   // mixed-radix Stockham FFT when n_fft/2 (even) or n_fft (odd) is 5-smooth and the buffers fit
+            KbMrParams q{};
+            q.half = (plan->n_fft & 1) ? 0 : 1;
+            q.P = q.half ? plan->n_fft / 2 : plan->n_fft;
+            q.n_pass = kb_mr_factor(q.P, q.radix);
+            int NW = 8;
+            while (NW >= 1 && kb_mr_smem_layout(q.P, NW).total > plan->dev.smem_optin) NW >>= 1;
+            if (q.n_pass >= 0 && NW >= 1 && kb_env_int("KAPRE_B200_NOMR", 0) == 0) {
+                const int smem = kb_mr_smem_layout(q.P, NW).total;
+                int bps = (228 * 1024) / (smem + 1024);
+                if (bps > 16 / NW) bps = 16 / NW;
+                if (bps < 1) bps = 1;
+                q.d = p; q.d.n_warps = NW;
+                q.TF = 4 * NW;
+                if ((rc = kb_set_smem(kb_mr_kernel, smem))) return rc;
+                const long long tiles = (long long)B * C * ((T + q.TF - 1) / q.TF);
+                const long long gmax = (long long)plan->dev.sm_count * bps;
+                const int grid = (int)(tiles < gmax ? tiles : gmax);
+                KbProfScope prof(st);
+                kb_mr_kernel<<<grid, NW * 32, smem, st>>>(q);
+                KB_CUDA(cudaGetLastError());
+                g_launches++;
+                char buf[160];
+                snprintf(buf, sizeof(buf), "MR P%d passes%d NW%d grid%d smem%d bps%d", q.P, q.n_pass, NW, grid, smem, bps);
+                g_launch_info = buf;
+                return 0;
+            }
+        }
         const KbDftSmem L = kb_dft_smem_layout(plan->n_fft, plan->win_eff);
-        if (L.total > plan->dev.smem_optin) return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d too large for the direct-DFT kernel", plan->n_fft);
+        if (L.total > plan->dev.smem_optin) return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d has a prime factor above 5 and is too large for the direct-DFT kernel (%d B of shared memory needed)", plan->n_fft, L.total);
         if ((rc = kb_set_smem(kb_dft_kernel, L.total))) return rc;
         long long tiles = (long long)B * C * p.n_tiles_t;
         int grid = (int)(tiles < plan->dev.sm_count * 4LL ? tiles : plan->dev.sm_count * 4LL);
         kb_dft_kernel<<<grid, 256, L.total, st>>>(p);
         KB_CUDA(cudaGetLastError());
         g_launches++;
+        {
+            char buf[96];
+            snprintf(buf, sizeof(buf), "DFT n_fft%d grid%d smem%d (direct O(N^2): prime factor > 5)", plan->n_fft, grid, L.total);
+            g_launch_info = buf;
+        }
         return 0;
     }
 
@@ -1059,10 +1098,11 @@ int kapre_apply_filterbank(const kapre_filterbank* fb, const float* x_dev, int b
     p.B = batch; p.C = channels; p.T = frames; p.F = fb->n_freq;
     p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands;
     p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
-    p.n_tiles_t = (frames + 31) / 32; p.n_warps = 8;
-    const KbFbSmem L = kb_fb_smem_layout(fb->n_freq, fb->n_bands);
-    if (L.total > fb->dev.smem_optin)
+    p.R = kb_fb_pick_r(fb->n_freq, fb->n_bands, fb->dev.smem_optin);
+    if (p.R == 0)
         return kb_fail(KAPRE_E_UNSUPPORTED, "filterbank %dx%d does not fit shared memory", fb->n_freq, fb->n_bands);
+    p.n_tiles_t = (frames + p.R - 1) / p.R; p.n_warps = 8;
+    const KbFbSmem L = kb_fb_smem_layout(fb->n_freq, fb->n_bands, p.R);
     if ((rc = kb_set_smem(kb_fb_kernel, L.total))) return rc;
     int bps = (228 * 1024) / (L.total + 1024);
     if (bps > 8) bps = 8;
@@ -1203,7 +1243,7 @@ int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_ite
 // column 1 (Im of k1 = 0, identically zero), which carries the real k1 = 16 sum.  store == 0 (timing): out must
 // hold grid * 256 floats of checksums; *grid_out receives the grid size.  T = 1 + (length - 1024) / 256.
 int kapre_tc_dft_stage1(const float* x_dev, int n_items, long long item_stride, int length, float* out_dev, int store,
-                        int* grid_out, void* stream) {
+                        int* grid_out, const float* fmat_override_dev, void* stream) {
     if (!x_dev || !out_dev) return kb_fail(KAPRE_E_INVALID, "null data pointer");
     if (n_items < 1 || length < KB_TC_NFFT) return kb_fail(KAPRE_E_INVALID, "need n_items >= 1 and length >= 1024");
     DevInfo dev;
@@ -1232,7 +1272,8 @@ int kapre_tc_dft_stage1(const float* x_dev, int n_items, long long item_stride, 
     KbTcParams p{};
     p.x = x_dev; p.item_stride = item_stride; p.n_items = n_items; p.length = length;
     p.T = 1 + (length - KB_TC_NFFT) / KB_TC_HOP;
-    p.out = out_dev; p.store = store; p.fmat = d_fmat[dev.device];
+    p.out = out_dev; p.store = store;
+    p.fmat = fmat_override_dev ? fmat_override_dev : d_fmat[dev.device];   // override: layout debugging (2048 floats)
     p.n_tiles_t = (p.T + KB_TC_TILE_F - 1) / KB_TC_TILE_F;
     const long long tiles = (long long)n_items * p.n_tiles_t;
     const long long gmax = (long long)dev.sm_count * 2;

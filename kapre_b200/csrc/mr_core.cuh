@@ -1,0 +1,219 @@
+// Mixed-radix (2, 3, 4, 5) Stockham FFT for every n_fft the register kernel (n_fft = 64 * {4, 8, 16, 32}) does not
+// take: the reference's own tests use n_fft = 1000 = 2^3 5^3 (tests/test_time_frequency.py:72-125), speech front
+// ends 400, music 4096 / 8192.  Same semantics as kapre/time_frequency.py:169-182 (pad_begin, right zero-pad of a
+// short window to n_fft, rfft).
+//
+// One warp transforms one frame at a time in shared memory:
+//   even n_fft: packed real FFT -- complex FFT of length P = n_fft / 2 of z[n] = x[2n] + i x[2n+1], then the pair step
+//               X[k], X[P-k] from Z[k], Z[P-k] (as in stft_core.cuh);   odd n_fft: complex FFT of length P = n_fft.
+//   Stockham autosort passes (ping-pong between two P-point buffers, natural order in and out), pass with radix r
+//   after radices of product Ns:   lane j < P / r:  k = j mod Ns,
+//       v[t] = in[j + t P / r] * exp(-2 pi i t k / (Ns r)),  V = DFT_r(v),  out[(j - k) r + k + t Ns] = V[t]
+//   twiddles from one shared table exp(-2 pi i m / P).
+// Instruction count per frame is about 1.5x the register kernel's at the neighbouring power of two (4 passes over
+// shared memory instead of 1 transpose), against ~100x for the direct O(N^2) DFT it replaces (kb_dft_cta stays for
+// sizes with a prime factor > 5).
+#pragma once
+#include "aux_core.cuh"
+
+#define KB_MR_MAX_PASS 12
+
+struct KbMrParams {
+    KbDftParams d;            // tensors, sizes, window (w[0, win_eff)), tw = exp(-2 pi i r / n_fft), mode, n_warps
+    int P;                    // complex FFT length: n_fft / 2 (even n_fft) or n_fft
+    int half;                 // 1: packed real FFT (even n_fft)
+    int n_pass;
+    int radix[KB_MR_MAX_PASS];
+    int TF;                   // frames per tile (= frames per warp per tile * n_warps)
+};
+
+// radices of P in {4, 2, 3, 5} order (4s first: fewest passes); returns -1 if P has another prime factor
+static inline int kb_mr_factor(int P, int* radix) {
+    int n = 0;
+    while (P % 4 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 4; P /= 4; }
+    while (P % 2 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 2; P /= 2; }
+    while (P % 3 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 3; P /= 3; }
+    while (P % 5 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 5; P /= 5; }
+    return P == 1 ? n : -1;
+}
+
+struct KbMrSmem { int tw, buf, total; };
+KB_HD KbMrSmem kb_mr_smem_layout(int P, int n_warps) {
+    KbMrSmem s;
+    s.tw = 0;
+    s.buf = kb_align16(P * 8);
+    s.total = s.buf + n_warps * 2 * kb_align16(P * 8);
+    return s;
+}
+
+KB_HD cpx kb_mul_mi(cpx a) { return cmake(a.im, -a.re); }   // a * (-i)
+
+// forward DFTs of size r on v[0..r)
+KB_HD void kb_dft_r2(cpx* v) { const cpx a = v[0], b = v[1]; v[0] = cadd(a, b); v[1] = csub(a, b); }
+KB_HD void kb_dft_r4(cpx* v) {
+    const cpx a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = kb_mul_mi(csub(v[1], v[3]));
+    v[0] = cadd(a, c); v[2] = csub(a, c); v[1] = cadd(b, d); v[3] = csub(b, d);
+}
+KB_HD void kb_dft_r3(cpx* v) {
+    const cpx t1 = cadd(v[1], v[2]);
+    const cpx m1 = cfma_s(t1, -0.5f, v[0]);
+    const cpx m2 = kb_mul_mi(cscale(csub(v[1], v[2]), 0.86602540378443864676f));
+    v[0] = cadd(v[0], t1); v[1] = cadd(m1, m2); v[2] = csub(m1, m2);
+}
+KB_HD void kb_dft_r5(cpx* v) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    const cpx a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    const cpx r1 = cfma_s(a2, c2, cfma_s(a1, c1, v[0])), r2 = cfma_s(a2, c1, cfma_s(a1, c2, v[0]));
+    const cpx q1 = kb_mul_mi(cfma_s(b2, s2, cscale(b1, s1))), q2 = kb_mul_mi(cfma_s(b2, -s1, cscale(b1, s2)));
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = cadd(r1, q1); v[4] = csub(r1, q1);
+    v[2] = cadd(r2, q2); v[3] = csub(r2, q2);
+}
+
+// one Stockham pass of radix RDX for the calling lane (all butterflies j = lane, lane + 32, ...)
+template <int RDX>
+KB_FN void kb_mr_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw_s, int P, int Ns, int lane) {
+    const int nb = P / RDX;                 // butterflies
+    const int tstep = P / (Ns * RDX);       // exp(-2 pi i t k / (Ns r)) = tw_s[t k tstep]
+    int k = lane % Ns;                      // j mod Ns, stepped with j (one division per pass, not per butterfly)
+    const int kinc = 32 % Ns;
+    for (int j = lane; j < nb; j += 32, k = (k + kinc >= Ns) ? k + kinc - Ns : k + kinc) {
+        cpx v[RDX];
+#pragma unroll
+        for (int t = 0; t < RDX; ++t) v[t] = in[j + t * nb];
+        if (Ns > 1) {
+#pragma unroll
+            for (int t = 1; t < RDX; ++t) v[t] = cmul(v[t], tw_s[t * k * tstep]);
+        }
+        if (RDX == 2) kb_dft_r2(v);
+        else if (RDX == 3) kb_dft_r3(v);
+        else if (RDX == 4) kb_dft_r4(v);
+        else kb_dft_r5(v);
+        const int j0 = (j - k) * RDX + k;
+#pragma unroll
+        for (int t = 0; t < RDX; ++t) out[j0 + t * Ns] = v[t];
+    }
+}
+
+#if defined(KB_HOST_EMU)
+inline void kb_mr_cta(const KbMrParams& q, char* smem, int cta, int n_cta)
+#else
+__device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int cta, int n_cta)
+#endif
+{
+    const KbDftParams& p = q.d;
+    const int NW = p.n_warps;
+    const int kb_nt = NW * 32;
+    (void)kb_nt;
+    const int N = p.n_fft, We = p.win_eff, F = N / 2 + 1, P = q.P;
+    const KbMrSmem L = kb_mr_smem_layout(P, NW);
+    cpx* tw_s = reinterpret_cast<cpx*>(smem + L.tw);
+    const int bufsz = kb_align16(P * 8);
+    const int n_tiles_t = (p.T + q.TF - 1) / q.TF;
+    const int n_tiles = p.B * p.C * n_tiles_t;
+    const int fpw = q.TF / NW;               // frames per warp and tile
+#if defined(KB_HOST_EMU)
+    std::vector<KbThreadRegs> kb_regs(kb_nt);
+#else
+    KbThreadRegs kb_regs;
+#endif
+    KB_PHASE_BEGIN
+        (void)R;
+        const int st = q.half ? 2 : 1;
+        for (int i = tid; i < P; i += kb_nt) { float2 t = p.tw[i * st]; tw_s[i] = cmake(t.x, t.y); }
+    KB_PHASE_END
+    KB_SYNC_CTA;
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+        const int sig = tile / n_tiles_t;
+        const int tt = tile - sig * n_tiles_t;
+        const int b = sig / p.C, c = sig - b * p.C;
+        const float* xsig = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc;
+        const long long obase = (long long)b * p.o_sb + (long long)c * p.o_sc;
+        for (int fi = 0; fi < fpw; ++fi) {
+            // every step below is private to one warp (its own two buffers): warp-level synchronisation only
+            KB_PHASE_BEGIN
+                (void)R;
+                const int warp = tid >> 5, lane = tid & 31;
+                const int t = tt * q.TF + warp * fpw + fi;
+                cpx* A = reinterpret_cast<cpx*>(smem + L.buf + (warp * 2) * bufsz);
+                if (t < p.T) {
+                    const long long s0 = (long long)t * p.hop - p.pad_left;
+                    if (q.half) {
+                        for (int n = lane; n < P; n += 32) {
+                            float v[2];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int m = 2 * n + h;
+                                const long long s = s0 + m;
+                                v[h] = (m < We && s >= 0 && s < p.L) ? kb_ldg(xsig + s * p.x_sl) * kb_ldg(p.w + m) : 0.0f;
+                            }
+                            A[n] = cmake(v[0], v[1]);
+                        }
+                    } else {
+                        for (int n = lane; n < P; n += 32) {
+                            const long long s = s0 + n;
+                            const float v = (n < We && s >= 0 && s < p.L) ? kb_ldg(xsig + s * p.x_sl) * kb_ldg(p.w + n) : 0.0f;
+                            A[n] = cmake(v, 0.0f);
+                        }
+                    }
+                }
+            KB_PHASE_END
+            KB_SYNC_WARP;
+            int Ns = 1;
+            for (int ps = 0; ps < q.n_pass; ++ps) {
+                const int r = q.radix[ps];
+                KB_PHASE_BEGIN
+                    (void)R;
+                    const int warp = tid >> 5, lane = tid & 31;
+                    const int t = tt * q.TF + warp * fpw + fi;
+                    cpx* b0 = reinterpret_cast<cpx*>(smem + L.buf + (warp * 2) * bufsz);
+                    cpx* b1 = reinterpret_cast<cpx*>(smem + L.buf + (warp * 2 + 1) * bufsz);
+                    const cpx* in = (ps & 1) ? b1 : b0;
+                    cpx* out = (ps & 1) ? b0 : b1;
+                    if (t < p.T) {
+                        if (r == 4) kb_mr_pass<4>(in, out, tw_s, P, Ns, lane);
+                        else if (r == 2) kb_mr_pass<2>(in, out, tw_s, P, Ns, lane);
+                        else if (r == 3) kb_mr_pass<3>(in, out, tw_s, P, Ns, lane);
+                        else kb_mr_pass<5>(in, out, tw_s, P, Ns, lane);
+                    }
+                KB_PHASE_END
+                KB_SYNC_WARP;
+                Ns *= r;
+            }
+            KB_PHASE_BEGIN
+                (void)R;
+                const int warp = tid >> 5, lane = tid & 31;
+                const int t = tt * q.TF + warp * fpw + fi;
+                const cpx* Z = reinterpret_cast<const cpx*>(smem + L.buf + (warp * 2 + (q.n_pass & 1)) * bufsz);
+                if (t < p.T) {
+                    const long long o = obase + (long long)t * p.o_st;
+                    float2* oc = reinterpret_cast<float2*>(p.out) + o;
+                    float* orl = reinterpret_cast<float*>(p.out) + o;
+                    if (q.half) {
+                        // X[k] = (Z[k] + conj Z[P-k]) / 2 - i/2 exp(-2 pi i k / N) (Z[k] - conj Z[P-k]),  k = 0 .. P
+                        for (int k = lane; k <= P; k += 32) {
+                            const cpx a = Z[k == P ? 0 : k];
+                            const cpx bq = Z[k == 0 || k == P ? 0 : P - k];
+                            const cpx e = cadd_conj(a, bq), dd = csub_conj(a, bq);
+                            float2 w2;
+                            if (k == P) w2 = make_float2(-1.0f, 0.0f);
+                            else { w2.x = kb_ldg(reinterpret_cast<const float*>(p.tw + k)); w2.y = kb_ldg(reinterpret_cast<const float*>(p.tw + k) + 1); }
+                            const cpx tq = cmul(cmake(dd.im, -dd.re), cmake(w2.x, w2.y));
+                            const cpx X = cscale(cadd(e, tq), 0.5f);
+                            if (p.mode == KB_OUT_COMPLEX) oc[(long long)k * p.o_sk] = make_float2(X.re, X.im);
+                            else orl[(long long)k * p.o_sk] = kb_sqrt(cnorm(X));
+                        }
+                    } else {
+                        for (int k = lane; k < F; k += 32) {
+                            const cpx X = Z[k];
+                            if (p.mode == KB_OUT_COMPLEX) oc[(long long)k * p.o_sk] = make_float2(X.re, X.im);
+                            else orl[(long long)k * p.o_sk] = kb_sqrt(cnorm(X));
+                        }
+                    }
+                }
+            KB_PHASE_END
+            KB_SYNC_WARP;
+        }
+    }
+}

@@ -7,9 +7,10 @@
 // Stage 1 as ONE GEMM per tile of 4 frames:  D[(f, n2), c] = A[(f, n2), n1] . F[n1, c],  M = 128, K = 32, N = 32.
 //   * A is the RAW hop-overlapped sample buffer: element ((f, n2), n1) = x[32 (8 f + n1) + n2], i.e. the
 //     natural [row of 32 samples][32] view is exactly an MN-major operand with 128-byte K rows -- the
-//     SWIZZLE_128B MN-major canonical layout of the UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp:
-//     ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).  Frames overlap: the M-group stride (LBO) is hop * 4 bytes,
-//     a K step of 8 rows advances the start address by 1024 bytes.  No per-frame copy of the samples is made.
+//     SWIZZLE_128B_BASE32B MN-major canonical layout of the UMMA shared-memory descriptor (the one TF32 MN-major
+//     operands must use; cute/atom/mma_traits_sm100.hpp Layout_MN_SW128_32B_Atom: atoms of 4 K rows x 128 bytes).
+//     Frames overlap: the M-group stride (LBO) is hop * 4 bytes, a K step of 8 rows advances the start address by
+//     1024 bytes.  No per-frame copy of the samples is made.
 //   * x is real, so only k1 = 0..16 are needed: columns c = (Re, Im) of k1 = 0..15; the identically-zero
 //     Im(k1 = 0) column carries k1 = 16 (also real), so N = 32 with no padding.
 //   * fp32-grade accuracy from TF32 operands by the 3-product split (hi = top 19 bits, lo = exact remainder):
@@ -92,9 +93,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// byte offset of sample (row u, column c) inside a SWIZZLE_128B buffer of 128-byte rows (1024 B-aligned base)
+// byte offset of sample (row u, column c) inside a buffer of 128-byte rows in the SWIZZLE_128B_BASE32B pattern --
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout" (cutlass sm100_common.inl:92):
+// cute Swizzle<2,5,2>: the 32-byte unit index (address bits 5-6) is XORed with the row index mod 4 (bits 7-8).
 __device__ __forceinline__ uint32_t swz(uint32_t u, uint32_t c) {
-    return u * 128u + ((((c >> 2) ^ (u & 7u)) << 4) | ((c & 3u) << 2));
+    return u * 128u + ((((c >> 3) ^ (u & 3u)) << 5) | ((c & 7u) << 2));
 }
 
 }  // namespace kbtc
@@ -162,8 +165,9 @@ __global__ void __launch_bounds__(KB_TC_THREADS, 2) kb_tc_dft_stage1_kernel(cons
                 for (int j = 0; j < 4; ++j) {
                     // A: rows 8 (4 mt + f) + 8 j ..; M groups of 32 (one frame) are hop * 4 = 1024 bytes apart
                     const uint32_t aoff = (uint32_t)(mt * 4 * 1024 + j * 1024);
-                    const uint64_t a_hi = make_desc(a_hi_addr + aoff, 1024, 1024, 2);
-                    const uint64_t a_lo = make_desc(a_lo_addr + aoff, 1024, 1024, 2);
+                    // layout type 1 = SWIZZLE_128B_BASE32B: atoms of 4 K rows (SBO = 512 bytes between them)
+                    const uint64_t a_hi = make_desc(a_hi_addr + aoff, 1024, 512, 1);
+                    const uint64_t a_lo = make_desc(a_lo_addr + aoff, 1024, 512, 1);
                     // B (K-major, no swizzle): [kchunk][col][4]: 8-column groups 128 B apart (SBO), K chunks 512 B (LBO)
                     const uint64_t b_hi = make_desc(f_hi_addr + (uint32_t)(j * 1024), 512, 128, 0);
                     const uint64_t b_lo = make_desc(f_lo_addr + (uint32_t)(j * 1024), 512, 128, 0);

@@ -12,6 +12,7 @@
 #include "../../kapre_b200/csrc/stft_mc_core.cuh"
 #include "../../kapre_b200/csrc/istft_core.cuh"
 #include "../../kapre_b200/csrc/aux_core.cuh"
+#include "../../kapre_b200/csrc/mr_core.cuh"
 
 template <int Q, int MODE>
 static void run_stft_qm(const KbStftParams& p, int n_cta) {
@@ -248,6 +249,35 @@ int kb_emu_dft(const float* x, long long x_sb, long long x_sc, long long x_sl, i
     return 0;
 }
 
+// Mixed-radix Stockham kernel (mr_core.cuh).  Returns -3 when n_fft has a prime factor > 5.
+int kb_emu_mr(const float* x, long long x_sb, long long x_sc, long long x_sl, int B, int C, int L,
+              int n_fft, int win_length, int hop, int pad_left, int T, const float* window, int mode,
+              void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk, int n_warps, int fpw, int n_cta) {
+    const int win_eff = win_length < n_fft ? win_length : n_fft;
+    std::vector<float2> tw(n_fft);
+    for (int r = 0; r < n_fft; ++r) {
+        const double a = -2.0 * M_PI * (double)r / (double)n_fft;
+        tw[r] = make_float2((float)cos(a), (float)sin(a));
+    }
+    KbMrParams q{};
+    KbDftParams& p = q.d;
+    p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
+    p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left; p.win_eff = win_eff; p.w = window; p.tw = tw.data();
+    p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode; p.n_warps = n_warps;
+    q.half = (n_fft & 1) ? 0 : 1;
+    q.P = q.half ? n_fft / 2 : n_fft;
+    q.n_pass = kb_mr_factor(q.P, q.radix);
+    if (q.n_pass < 0) return -3;
+    q.TF = fpw * n_warps;
+    const KbMrSmem L_ = kb_mr_smem_layout(q.P, n_warps);
+    std::vector<char> smem(L_.total + 64);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(smem.begin(), smem.end(), (char)0x7f);
+        kb_mr_cta(q, smem.data(), cta, n_cta);
+    }
+    return 0;
+}
+
 int kb_emu_idft(const float* X, long long x_sb, long long x_sc, long long x_st, long long x_sk, int B, int C, int T,
                 int n_fft, int win_length, int hop, const float* dual_window, float* y, long long y_sb,
                 long long y_sc, long long y_sl, int n_cta) {
@@ -275,15 +305,15 @@ int kb_emu_idft(const float* X, long long x_sb, long long x_sc, long long x_st, 
 
 int kb_emu_fb(const float* x, long long x_sb, long long x_sc, long long x_st, long long x_sk, int B, int C, int T,
               const float* fb, int n_freq, int n_bands, float* out, long long o_sb, long long o_sc, long long o_st,
-              long long o_sk, int n_cta) {
+              long long o_sk, int n_cta, int R) {
     std::vector<KbBand> bands; std::vector<float> fbw;
     kb_make_bands(fb, n_freq, n_bands, bands, fbw);
     KbFbParams p{};
     p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_st = x_st; p.x_sk = x_sk; p.B = B; p.C = C; p.T = T; p.F = n_freq;
     p.bands = bands.data(); p.fbw = fbw.data(); p.n_bands = n_bands;
     p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk;
-    p.n_tiles_t = (T + 31) / 32; p.n_warps = 8;
-    const KbFbSmem L_ = kb_fb_smem_layout(n_freq, n_bands);
+    p.R = R; p.n_tiles_t = (T + R - 1) / R; p.n_warps = 8;
+    const KbFbSmem L_ = kb_fb_smem_layout(n_freq, n_bands, R);
     std::vector<char> smem(L_.total + 64);
     for (int cta = 0; cta < n_cta; ++cta) {
         std::fill(smem.begin(), smem.end(), (char)0x7f);

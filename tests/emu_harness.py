@@ -176,6 +176,32 @@ def emu_dft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt,
     return out
 
 
+def emu_mr(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, out_fmt, n_warps=4, fpw=2, n_cta=3):
+    """Mixed-radix Stockham forward kernel body (mr_core.cuh kb_mr_cta): complex or magnitude output.
+    Returns None when n_fft has a prime factor above 5 (the library then uses the direct DFT)."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if in_fmt == 'channels_last':
+        B, L, C = x.shape
+        sb, sl, sc = L * C, C, 1
+    else:
+        B, C, L = x.shape
+        sb, sc, sl = C * L, L, 1
+    pad_left = (n_fft - hop) if pad_begin else 0
+    Lp = L + pad_left
+    T = -(-Lp // hop) if pad_end else max(0, 1 + (Lp - win_length) // hop)
+    shape, (osb, osc, ost, osk) = _strides4((B, C, T, n_fft // 2 + 1), out_fmt)
+    out = np.full(shape, np.nan, dtype=np.complex64 if mode == MODE_COMPLEX else np.float32)
+    window = np.ascontiguousarray(window, dtype=np.float32)
+    LL = ctypes.c_longlong
+    rc = lib.kb_emu_mr(_fp(x), LL(sb), LL(sc), LL(sl), B, C, L, n_fft, win_length, hop, pad_left, T, _fp(window),
+                       mode, _fp(out), LL(osb), LL(osc), LL(ost), LL(osk), n_warps, fpw, n_cta)
+    if rc == -3:
+        return None
+    assert rc == 0
+    return out
+
+
 def emu_idft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, n_cta=3):
     """Generic-n_fft inverse kernel body (kb_idft_cta)."""
     lib = load()
@@ -200,7 +226,7 @@ def emu_idft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, n_cta=3):
     return y
 
 
-def emu_fb(x, fb, fmt, n_cta=3):
+def emu_fb(x, fb, fmt, n_cta=3, R=32):
     """Stand-alone ApplyFilterbank kernel body (kb_fb_cta) on a (B, T, F, C) / (B, C, T, F) float tensor."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -215,6 +241,6 @@ def emu_fb(x, fb, fmt, n_cta=3):
     out = np.full(shape, np.nan, dtype=np.float32)
     LL = ctypes.c_longlong
     rc = lib.kb_emu_fb(_fp(x), LL(sb), LL(sc), LL(st), LL(sk), B, C, T, _fp(fb), fb.shape[0], M, _fp(out), LL(osb),
-                       LL(osc), LL(ost), LL(osk), n_cta)
+                       LL(osc), LL(ost), LL(osk), n_cta, R)
     assert rc == 0
     return out

@@ -138,6 +138,11 @@ def test_fuzz_generic_n_fft(n_fft, win_frac, hop, L, C, pad_begin, pad_end, fmt,
     out = E.emu_dft(x, n_fft, win, hop, w, pad_begin, pad_end, E.MODE_COMPLEX, fmt, fmt, n_cta=1 + seed % 3)
     assert out.shape == ref.shape
     assert _nerr(out, ref) < 5e-6
+    mr = E.emu_mr(x, n_fft, win, hop, w, pad_begin, pad_end, E.MODE_COMPLEX, fmt, fmt, n_warps=1 + seed % 4,
+                  fpw=1 + seed % 3, n_cta=1 + seed % 3)           # the Stockham kernel, when n_fft is 5-smooth
+    if mr is not None:
+        assert mr.shape == ref.shape
+        assert _nerr(mr, ref) < 5e-6
     if hop <= win:                  # the dual window needs overlapping (or abutting) frames
         dual = O.inverse_stft_window(win, hop, O.get_window(None, win))
         if np.isfinite(dual).all() and np.abs(dual).max() < 20:      # barely overlapping frames: 1/w blows up round-off

@@ -234,6 +234,34 @@ def test_emu_sixteen_warp_cta_n2048_mel():
     assert np.allclose(item_max, np.maximum(ref, 1e-5).reshape(2, -1).max(axis=1), rtol=3e-6)
 
 
+# ------------------------------------------------------------------------------- mixed-radix Stockham body
+@pytest.mark.parametrize('n_fft,win,hop', [(1000, 1000, 250), (1000, 512, 250), (400, 400, 160), (4096, 4096, 1024),
+                                           (100, 64, 33), (6, 6, 2), (2, 2, 1), (75, 75, 25), (135, 100, 40), (480, 480, 120),
+                                           (8192, 8192, 4096), (128, 128, 64), (3, 3, 1), (1, 1, 1)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_emu_mixed_radix_forward(n_fft, win, hop, fmt):
+    """mr_core.cuh: Stockham FFT with radices 2/3/4/5 for n_fft outside {256..2048}; packed real FFT for even
+    n_fft, complex FFT for odd (the reference's tests use n_fft = 1000, tests/test_time_frequency.py:72-125)."""
+    rng = np.random.default_rng(n_fft + hop)
+    x = wave(rng, 2, 2, max(3000, 2 * n_fft + 900) if n_fft > 50 else 200, fmt)
+    w = O.get_window(None, win).astype(np.float32)
+    for pads in ((False, False), (True, True)):
+        ref = O.stft_layer(x, n_fft, win, hop, None, pads[0], pads[1], fmt, fmt)
+        nw = 2 if n_fft >= 4096 else 4
+        out = E.emu_mr(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_COMPLEX, fmt, fmt, n_warps=nw, fpw=2)
+        assert out is not None and out.shape == ref.shape
+        assert nerr(out, ref) < 3e-6
+        mag = E.emu_mr(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_MAG, fmt, fmt, n_warps=nw, fpw=1, n_cta=2)
+        assert nerr(mag, np.abs(ref)) < 3e-6
+
+
+def test_emu_mixed_radix_rejects_large_prime_factors():
+    x = np.zeros((1, 1, 100), dtype=np.float32)
+    for n_fft in (14, 22, 98, 7):       # 7 | P or 11 | P
+        assert E.emu_mr(x, n_fft, n_fft, 1, np.ones(n_fft, np.float32), False, False, E.MODE_MAG, 'channels_first',
+                        'channels_first') is None
+
+
 # ------------------------------------------------------------------------------- stand-alone / generic-n_fft bodies
 @pytest.mark.parametrize('n_fft,win,hop', [(1000, 1000, 250), (1000, 512, 250), (400, 400, 160), (100, 64, 33), (6, 6, 2)])
 @pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
@@ -272,3 +300,5 @@ def test_emu_standalone_filterbank(fmt, F, M, kind):
     out = E.emu_fb(x, fb, fmt)
     assert out.shape == ref.shape
     assert nerr(out, ref) < 2e-6
+    for R in (16, 4, 1):          # shorter tiles: what long spectra (n_fft >= 4096) fall back to
+        assert nerr(E.emu_fb(x, fb, fmt, n_cta=2, R=R), ref) < 2e-6

@@ -117,6 +117,29 @@ def test_stft_short_window_golden(K, golden, pad_end):
     assert nerr(got, ref) < 5e-6
 
 
+@pytest.mark.parametrize('n_fft,win,hop,path', [(400, 400, 160, 'MR'), (1000, 1000, 250, 'MR'), (4096, 4096, 1024, 'MR'),
+                                                (8192, 8192, 2048, 'MR'), (16384, 16384, 4096, 'MR'), (75, 75, 25, 'MR'),
+                                                (480, 300, 120, 'MR'), (98, 98, 49, 'DFT'), (1022, 1022, 511, 'DFT')])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_stft_any_n_fft_mixed_radix(K, n_fft, win, hop, path, fmt):
+    """Every n_fft outside 64 * {4, 8, 16, 32}: the mixed-radix Stockham kernel when n_fft / 2 (even) or n_fft (odd)
+    is 5-smooth -- incl. 4096 / 8192 / 16384, which the direct-DFT kernel could not stage -- and the
+    direct DFT otherwise (a prime factor above 5)."""
+    rng = np.random.default_rng(n_fft)
+    x = wave(rng, 2, 2, max(6000, 2 * n_fft + 1000), fmt)
+    layer = K.STFT(n_fft=n_fft, win_length=win, hop_length=hop, pad_begin=True, pad_end=True,
+                   input_data_format=fmt, output_data_format=fmt)
+    got = layer(x)
+    info = K._native.last_launch_info()
+    assert info.startswith('MR ') == (path == 'MR'), info
+    ref = O.stft_layer(x, n_fft, win, hop, None, True, True, fmt, fmt)
+    assert got.shape == ref.shape
+    assert nerr(got, ref) < 3e-6
+    mag = K.get_stft_magnitude_layer(n_fft=n_fft, win_length=win, hop_length=hop, pad_begin=True, pad_end=True,
+                                     input_data_format=fmt, output_data_format=fmt)(x)
+    assert nerr(mag, np.abs(ref)) < 3e-6
+
+
 # ------------------------------------------------------------------------------- fused magnitude / mel / dB
 @pytest.mark.parametrize('n_fft,hop,n_mels,sr', [(512, 256, 64, 16000), (1024, 256, 128, 22050), (2048, 512, 128, 44100),
                                                   (256, 128, 20, 8000), (1024, 160, 80, 16000)])
