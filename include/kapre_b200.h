@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KAPRE_B200_VERSION 100
+#define KAPRE_B200_VERSION 200
 
 enum {
     KAPRE_OK = 0,
@@ -90,8 +90,9 @@ int kapre_stft_num_frames(const kapre_stft_plan* plan, int length, int pad_begin
 int kapre_stft_supports_mode(const kapre_stft_plan* plan, int mode);
 
 /* Enqueue the transform.  `fb` is required for KAPRE_OUT_FB / _FB_DB, `db` for *_DB.
- * `workspace_dev`: at least 4 * batch bytes, needed for *_DB (per-item maxima for the
- * dynamic-range clamp of kapre/backend.py:190-192); may be NULL otherwise.  The workspace is
+ * `workspace_dev`: at least 8 * batch bytes, needed for *_DB (per-item maxima for the
+ * dynamic-range clamp of kapre/backend.py:190-192 + per-item arrival counters of the clamp pass, which
+ * runs several CTAs per long item); may be NULL otherwise.  The workspace is
  * SELF-CLEANING: it must be all-zero when first passed in (cudaMemset once after allocation)
  * and every call leaves it all-zero again, so it can be reused by later calls on the same
  * stream without further memsets. */
@@ -126,7 +127,7 @@ int kapre_magnitude(const void* x_complex_dev, float* out_dev, int64_t n, void* 
 int kapre_phase(const void* x_complex_dev, float* out_dev, int64_t n, void* stream);
 /* backend.magnitude_to_decibel on a contiguous (n_items, item_size) tensor: the maximum for the
  * dynamic-range clamp is taken per item (kapre/backend.py:178-192); pass n_items = 1 for a
- * 1-D input (global maximum).  workspace_dev: >= 4 * n_items bytes, zero on entry, left zero
+ * 1-D input (global maximum).  workspace_dev: >= 8 * n_items bytes, zero on entry, left zero
  * (self-cleaning, see kapre_stft_forward).  In-place is allowed. */
 int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_items, int64_t item_size,
                                const kapre_db_cfg* db, void* workspace_dev, void* stream);

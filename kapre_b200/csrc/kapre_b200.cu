@@ -141,36 +141,44 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_idft_kernel(const __grid
 
 // Dynamic-range clamp, kapre/backend.py:190-192: y = max(y, max_item(y) - dynamic_range).
 // item_max holds max(x, amin) per item (uint view); log is monotone, so the item maximum in
-// dB is dB(item_max).  One CTA per item: it reads the maximum, RESETS it to zero (the workspace
-// is self-cleaning: zero before the first use, zero again after every call) and returns
-// immediately when the clamp cannot bind (threshold <= dB(amin)), which is the common case
-// (SURVEY section 7), so no output byte is re-read.  Launched with programmatic dependent
-// launch: the grid is scheduled while the producer kernel drains.
+// dB is dB(item_max).  `chunks` CTAs per item (so that one long item is rewritten by many CTAs when the
+// clamp binds): each reads the maximum and returns immediately when the clamp cannot bind (threshold <=
+// dB(amin)), which is the common case, so no output byte is re-read.  The workspace is
+// SELF-CLEANING: words [0, n_items) are the maxima, words [n_items, 2 n_items) count the CTAs of an item that
+// have read its maximum; the last one resets both to zero.  A NaN anywhere in an item makes its maximum NaN
+// (the producers keep NaN through their max()), and tf.maximum(y, NaN) is NaN for the whole item.
+// Launched with programmatic dependent launch: the grid is scheduled while the producer kernel drains.
 __global__ void kb_db_clamp_kernel(float* __restrict__ y, long long item_size, long long run, long long period,
-                                   unsigned int* __restrict__ item_max, float amin,
+                                   unsigned int* __restrict__ item_max, unsigned int n_items, int chunks, float amin,
                                    float db_mul, float db_sub, float dyn_range) {
 #if __CUDA_ARCH__ >= 900
     asm volatile("griddepcontrol.launch_dependents;");   // the next fused kernel may start its table prologue
     cudaGridDependencySynchronize();
 #endif
-    const long long item = blockIdx.x;
+    const long long item = blockIdx.x / chunks;
+    const int chunk = (int)(blockIdx.x - item * chunks);
     __shared__ unsigned int s_mx;
-    if (threadIdx.x == 0) {
-        s_mx = item_max[item];
-        item_max[item] = 0u;
-    }
+    if (threadIdx.x == 0) s_mx = item_max[item];
     __syncthreads();
+    if (threadIdx.x == 0) {
+        // every CTA of the item has its copy of the maximum before the last arrival clears it
+        unsigned int* cnt = item_max + n_items + item;
+        if (chunks == 1 || atomicAdd(cnt, 1u) == (unsigned int)(chunks - 1)) {
+            item_max[item] = 0u;
+            if (chunks > 1) *cnt = 0u;
+        }
+    }
     const float mx = __uint_as_float(s_mx);
-    const float thr = (db_mul * __log2f(fmaxf(mx, amin)) - db_sub) - dyn_range;
+    float thr = (db_mul * __log2f(fmaxf(mx, amin)) - db_sub) - dyn_range;
     const float floor_db = db_mul * __log2f(amin) - db_sub;
-    if (!(thr > floor_db)) return;
+    const bool nan_item = mx != mx;
+    if (!nan_item && !(thr > floor_db)) return;
+    if (nan_item) thr = mx;
     float* yi = y + item * item_size;
+    const long long step = (long long)chunks * blockDim.x;
     // only elements with (i mod period) < run are decibel values (magnitude half of a mag+phase tensor)
-    if (run >= period) {
-        for (long long i = threadIdx.x; i < item_size; i += blockDim.x) yi[i] = fmaxf(yi[i], thr);
-    } else {
-        for (long long i = threadIdx.x; i < item_size; i += blockDim.x)
-            if (i % period < run) yi[i] = fmaxf(yi[i], thr);
+    for (long long i = (long long)chunk * blockDim.x + threadIdx.x; i < item_size; i += step) {
+        if (run >= period || i % period < run) yi[i] = nan_item ? thr : fmaxf(yi[i], thr);
     }
 }
 
@@ -182,14 +190,15 @@ __global__ void kb_db_kernel(const float* __restrict__ x, float* __restrict__ y,
     const int chunk = blockIdx.x - (int)(item * chunks);
     const float* xi = x + item * item_size;
     float* yi = y + item * item_size;
-    float mx = 0.0f;
+    unsigned int mxu = 0u;
     for (long long i = (long long)chunk * blockDim.x + threadIdx.x; i < item_size;
          i += (long long)chunks * blockDim.x) {
-        const float v = fmaxf(xi[i], amin);
-        mx = fmaxf(mx, v);
+        const float xv = xi[i];
+        const float v = xv < amin ? amin : xv;               // max that keeps NaN (tf.maximum propagates it)
+        mxu = max(mxu, __float_as_uint(v));                    // v > 0 or NaN: the uint order is the float order, NaN on top
         yi[i] = db_mul * __log2f(v) - db_sub;
     }
-    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    const unsigned int wm = __reduce_max_sync(0xffffffffu, mxu);
     if ((threadIdx.x & 31) == 0 && wm != 0u) atomicMax(item_max + item, wm);
 }
 
@@ -598,10 +607,14 @@ static int kb_launch_clamp(float* y, long long n_items, long long item_size, uns
                            float amin, float db_mul, float db_sub, float dr, cudaStream_t st,
                            long long run = 1, long long period = 1) {
     if (n_items <= 0 || item_size <= 0) return 0;
-    if (n_items > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items for the clamp kernel");
+    // one CTA per 32 Ki elements of an item (at most 64): a binding clamp on a long item is rewritten in parallel
+    long long chunks = (item_size + 32767) / 32768;
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    if (n_items * chunks > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many items for the clamp kernel");
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)n_items);
-    cfg.blockDim = dim3(128);
+    cfg.gridDim = dim3((unsigned)(n_items * chunks));
+    cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -609,7 +622,8 @@ static int kb_launch_clamp(float* y, long long n_items, long long item_size, uns
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = kb_env_int("KAPRE_B200_PDL", 1) ? 1 : 0;
-    KB_CUDA(cudaLaunchKernelEx(&cfg, kb_db_clamp_kernel, y, item_size, run, period, item_max, amin, db_mul, db_sub, dr));
+    KB_CUDA(cudaLaunchKernelEx(&cfg, kb_db_clamp_kernel, y, item_size, run, period, item_max, (unsigned int)n_items,
+                               (int)chunks, amin, db_mul, db_sub, dr));
     g_launches++;
     return 0;
 }
@@ -760,10 +774,25 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         if (plan->Q && fb->Q != plan->Q) return kb_fail(KAPRE_E_INVALID, "filterbank was not prepared for n_fft=%d", plan->n_fft);
     }
     float db_mul = 0, db_sub = 0;
+    long long db_item_size = 0, db_run = 1, db_period = 1;
     if (dbmode) {
         if ((rc = kb_check_db(db))) return rc;
         if (!workspace_dev) return kb_fail(KAPRE_E_INVALID, "workspace required for decibel modes");
         kb_db_consts(db, &db_mul, &db_sub);
+        // Output layout of the clamp pass, checked BEFORE anything is launched (a late failure would leave
+        // per-item maxima in the self-cleaning workspace).  Items are contiguous blocks of stride_b elements
+        // in both data formats.
+        const long long K = fbmode ? fb->n_bands : (plan->n_fft / 2 + 1);
+        const long long chans = (mode == KAPRE_OUT_MAG_PHASE) ? 2LL * C : C;
+        db_item_size = chans * T * K;
+        if (od->stride_b != db_item_size)
+            return kb_fail(KAPRE_E_UNSUPPORTED, "decibel modes need a batch-contiguous output (stride_b=%lld, item=%lld)",
+                           (long long)od->stride_b, db_item_size);
+        if (mode == KAPRE_OUT_MAG_PHASE) {   // clamp only the magnitude channels [0, C) of the 2C-channel item
+            if (od->stride_c == 1 && od->stride_f == chans && od->stride_t == K * chans) { db_run = C; db_period = chans; }
+            else if (od->stride_f == 1 && od->stride_t == K && od->stride_c == (long long)T * K) { db_run = (long long)C * T * K; db_period = db_item_size; }
+            else return kb_fail(KAPRE_E_UNSUPPORTED, "mag+phase decibel output must be a contiguous channels_first or channels_last tensor");
+        }
     }
     const int pad_left = pad_begin ? (plan->n_fft - plan->hop) : 0;
 
@@ -917,23 +946,9 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
                  cfg.TF, cfg.NW, use_mc ? 0 : (int)bulk, grid, cfg.smem, cfg.bps, tiles, use_mc ? 0 : fbmma);
         g_launch_info = buf;
     }
-    if (dbmode) {
-        // items are contiguous blocks of stride_b elements in both data formats
-        const long long K = fbmode ? fb->n_bands : (plan->n_fft / 2 + 1);
-        const long long chans = (mode == KAPRE_OUT_MAG_PHASE) ? 2LL * C : C;
-        const long long item_size = chans * T * K;
-        if (od->stride_b != item_size)
-            return kb_fail(KAPRE_E_UNSUPPORTED, "decibel modes need a batch-contiguous output (stride_b=%lld, item=%lld)",
-                           (long long)od->stride_b, item_size);
-        long long run = 1, period = 1;
-        if (mode == KAPRE_OUT_MAG_PHASE) {   // clamp only the magnitude channels [0, C) of the 2C-channel item
-            if (od->stride_c == 1 && od->stride_f == chans && od->stride_t == K * chans) { run = C; period = chans; }
-            else if (od->stride_f == 1 && od->stride_t == K && od->stride_c == (long long)T * K) { run = (long long)C * T * K; period = item_size; }
-            else return kb_fail(KAPRE_E_UNSUPPORTED, "mag+phase decibel output must be a contiguous channels_first or channels_last tensor");
-        }
-        rc = kb_launch_clamp((float*)out_dev, B, item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
-                             db->dynamic_range, st, run, period);
-    }
+    if (dbmode)
+        rc = kb_launch_clamp((float*)out_dev, B, db_item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
+                             db->dynamic_range, st, db_run, db_period);
     return rc;
 }
 

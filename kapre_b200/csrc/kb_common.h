@@ -221,5 +221,20 @@ KB_HD float cnorm(cpx a) {
 #endif
 }
 
+// Decibel epilogues: tf.maximum / tf.reduce_max propagate NaN (kapre/backend.py:186-192), fmaxf does not.
+//   kb_floor_keepnan(v, amin) = max(v, amin) that keeps a NaN v;
+//   kb_max_keepnan(a, b): both arguments are positive (>= amin) or NaN, so the unsigned order of the bit patterns
+//   is the float order with NaN on top -- an integer max (and the per-item atomicMax works on the same view).
+KB_HD float kb_floor_keepnan(float v, float amin) { return v < amin ? amin : v; }
+KB_HD float kb_max_keepnan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(max(__float_as_uint(a), __float_as_uint(b)));
+#else
+    uint32_t ua, ub;
+    std::memcpy(&ua, &a, 4); std::memcpy(&ub, &b, 4);
+    return ua > ub ? a : b;
+#endif
+}
+
 // shared-memory footprint helpers (bytes), shared by host launch code and kernels
 KB_HD int kb_align16(int v) { return (v + 15) & ~15; }

@@ -749,10 +749,10 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                                     if (kk >= 0) orl[(long long)kk * sk + p.ph_off] = kb_atan2(-X2.im, X2.re);
                                 }
                                 if (dbany) {
-                                    m1 = fmaxf(m1, p.amin);
-                                    m2 = fmaxf(m2, p.amin);
-                                    R.runmax = fmaxf(R.runmax, m1);
-                                    if (kk >= 0) R.runmax = fmaxf(R.runmax, m2);
+                                    m1 = kb_floor_keepnan(m1, p.amin);
+                                    m2 = kb_floor_keepnan(m2, p.amin);
+                                    R.runmax = kb_max_keepnan(R.runmax, m1);
+                                    if (kk >= 0) R.runmax = kb_max_keepnan(R.runmax, m2);
                                     m1 = p.db_mul * kb_log2(m1) - p.db_sub;
                                     m2 = p.db_mul * kb_log2(m2) - p.db_sub;
                                 }
@@ -889,8 +889,8 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                             if (dbmode) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
-                                    v[u] = fmaxf(v[u], amin);
-                                    rmax = fmaxf(rmax, v[u]);
+                                    v[u] = kb_floor_keepnan(v[u], amin);
+                                    rmax = kb_max_keepnan(rmax, v[u]);
                                     v[u] = dmul * (ftz ? kb_lg2_ftz(v[u]) : kb_log2(v[u])) - dsub;
                                 }
                             }
@@ -901,8 +901,8 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                             float v = srow[m];
                             if (fbmma) srow[m] = 0.0f;
                             if (dbmode) {
-                                v = fmaxf(v, amin);
-                                rmax = fmaxf(rmax, v);
+                                v = kb_floor_keepnan(v, amin);
+                                rmax = kb_max_keepnan(rmax, v);
                                 v = dmul * (ftz ? kb_lg2_ftz(v) : kb_log2(v)) - dsub;
                             }
                             orow[m] = v;
@@ -914,8 +914,8 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                             float v = srow[m];
                             if (fbmma) srow[m] = 0.0f;
                             if (dbmode) {
-                                v = fmaxf(v, amin);
-                                rmax = fmaxf(rmax, v);
+                                v = kb_floor_keepnan(v, amin);
+                                rmax = kb_max_keepnan(rmax, v);
                                 v = dmul * (ftz ? kb_lg2_ftz(v) : kb_log2(v)) - dsub;
                             }
                             *orow = v;

@@ -150,10 +150,10 @@ __device__ __forceinline__ void kb_mc_emit(const KbStftParams& p, bool dbany, vo
             if (kk >= 0) orl[kk * sk + p.ph_off] = kb_atan2(-X2.im, X2.re);
         }
         if (dbany) {
-            m1 = fmaxf(m1, p.amin);
-            m2 = fmaxf(m2, p.amin);
-            runmax = fmaxf(runmax, m1);
-            if (kk >= 0) runmax = fmaxf(runmax, m2);
+            m1 = kb_floor_keepnan(m1, p.amin);
+            m2 = kb_floor_keepnan(m2, p.amin);
+            runmax = kb_max_keepnan(runmax, m1);
+            if (kk >= 0) runmax = kb_max_keepnan(runmax, m2);
             m1 = p.db_mul * kb_log2(m1) - p.db_sub;
             m2 = p.db_mul * kb_log2(m2) - p.db_sub;
         }
@@ -698,8 +698,8 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
                         const int m = kb_fdiv(e, C, p.mc_magic_c), c = e - m * C;
                         float v = srow[c * L.Mp + m];
                         if (dbmode) {
-                            v = fmaxf(v, amin);
-                            rmax = fmaxf(rmax, v);
+                            v = kb_floor_keepnan(v, amin);
+                            rmax = kb_max_keepnan(rmax, v);
                             v = dmul * kb_log2(v) - dsub;
                         }
                         orow[e] = v;
@@ -716,8 +716,8 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
                     for (int m = lane; m < M; m += 32) {
                         float v = srow[m];
                         if (dbmode) {
-                            v = fmaxf(v, amin);
-                            rmax = fmaxf(rmax, v);
+                            v = kb_floor_keepnan(v, amin);
+                            rmax = kb_max_keepnan(rmax, v);
                             v = dmul * kb_log2(v) - dsub;
                         }
                         orow[(long long)m * sk] = v;

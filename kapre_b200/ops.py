@@ -59,19 +59,50 @@ def to_host(t: torch.Tensor) -> np.ndarray:
 
 
 _ws_cache = {}
+_ws_retired = []   # outgrown workspaces stay alive: a captured CUDA graph may have their address baked in
+
+
+def new_workspace(n_items: int, device) -> torch.Tensor:
+    """Zeroed scratch of the decibel modes: 2 words per item (maximum + clamp-pass arrival counter)."""
+    return torch.zeros(2 * max(int(n_items), 1), dtype=torch.int32, device=device)
 
 
 def _workspace(n_items: int, device) -> torch.Tensor:
     """Per-(device, stream) zero-initialised scratch for the per-item dB maxima.  The kernels leave
-    it zeroed (self-cleaning contract of the C ABI), so it is allocated and cleared only once."""
+    it zeroed (self-cleaning contract of the C ABI), so it is allocated and cleared only once.
+    Objects that record launches into a CUDA graph own a private workspace instead (``workspace=``
+    of ``stft_forward``), so nothing this cache does can invalidate a captured address."""
     n = max(int(n_items), 1)
     key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream().cuda_stream)
+           torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < n:
-        ws = torch.zeros(max(n, 1024), dtype=torch.int32, device=device)
+    if ws is None or ws.numel() < 2 * n:
+        if ws is not None:
+            _ws_retired.append(ws)
+        ws = new_workspace(max(n, 1024), device)
         _ws_cache[key] = ws
     return ws
+
+
+def _device_of_first_arg(fn):
+    """Run an op with the device of its first (tensor) argument current; host inputs keep the current device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(x, *a, **k):
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            with torch.cuda.device(x.device):
+                return fn(x, *a, **k)
+        return fn(x, *a, **k)
+    return wrapped
+
+
+def _on_device_of(t: torch.Tensor):
+    """Context that makes the tensor's device current: plans, filterbanks, workspaces and the launch
+    stream are all taken from the CURRENT device, which must be the one that owns the data."""
+    if not t.is_cuda:
+        raise N.KapreNativeError('kapre_b200 needs CUDA tensors (there is no CPU path)')
+    return torch.cuda.device(t.device)
 
 
 class _Handle:
@@ -206,11 +237,16 @@ def _spec_desc(t: torch.Tensor, data_format: str):
 
 
 def stft_forward(x: torch.Tensor, plan: StftPlan, input_data_format, output_data_format, pad_begin, pad_end,
-                 mode=N.OUT_COMPLEX, fb: Filterbank = None, db=None):
+                 mode=N.OUT_COMPLEX, fb: Filterbank = None, db=None, workspace: torch.Tensor = None):
     """One fused launch: waveform -> (complex STFT | magnitude | filterbank) [-> dB].
-    ``db`` = (ref_value, amin, dynamic_range)."""
+    ``db`` = (ref_value, amin, dynamic_range); ``workspace``: caller-owned decibel scratch (``new_workspace``)."""
     if not x.is_cuda:
         raise N.KapreNativeError('stft_forward needs a CUDA tensor')
+    with _on_device_of(x):
+        return _stft_forward(x, plan, input_data_format, output_data_format, pad_begin, pad_end, mode, fb, db, workspace)
+
+
+def _stft_forward(x, plan, input_data_format, output_data_format, pad_begin, pad_end, mode, fb, db, workspace):
     if x.dtype != torch.float32:
         x = x.float()
     if pad_begin and plan.hop_length > plan.n_fft:
@@ -227,16 +263,24 @@ def stft_forward(x: torch.Tensor, plan: StftPlan, input_data_format, output_data
     dbc, ws = None, None
     if mode in (N.OUT_MAG_DB, N.OUT_FB_DB) or (mode == N.OUT_MAG_PHASE and db is not None):
         dbc = N.DbCfg(float(db[0]), float(db[1]), float(db[2]))
-        ws = _workspace(B, x.device)
+        ws = workspace if workspace is not None else _workspace(B, x.device)
+        if ws.device != x.device or ws.numel() < 2 * B:
+            raise ValueError('decibel workspace must live on %s and hold 2 x %d words' % (x.device, B))
     if out.numel() == 0:
         return out
-    N.check(N.lib().kapre_stft_forward(
-        plan.handle(), _ptr(x), ctypes.byref(xd), int(bool(pad_begin)), int(bool(pad_end)), int(mode), _ptr(out),
-        ctypes.byref(od), fb.handle() if fbmode else None, ctypes.byref(dbc) if dbc is not None else None,
-        _ptr(ws) if ws is not None else None, _stream_ptr()))
+    try:
+        N.check(N.lib().kapre_stft_forward(
+            plan.handle(), _ptr(x), ctypes.byref(xd), int(bool(pad_begin)), int(bool(pad_end)), int(mode), _ptr(out),
+            ctypes.byref(od), fb.handle() if fbmode else None, ctypes.byref(dbc) if dbc is not None else None,
+            _ptr(ws) if ws is not None else None, _stream_ptr()))
+    except N.KapreNativeError:
+        if ws is not None and not torch.cuda.is_current_stream_capturing():
+            ws.zero_()          # a failed call may have left maxima behind: restore the all-zero contract
+        raise
     return out
 
 
+@_device_of_first_arg
 def istft(X: torch.Tensor, plan: IstftPlan, input_data_format, output_data_format):
     if not X.is_cuda:
         raise N.KapreNativeError('istft needs a CUDA tensor')
@@ -260,6 +304,7 @@ def istft(X: torch.Tensor, plan: IstftPlan, input_data_format, output_data_forma
     return y
 
 
+@_device_of_first_arg
 def apply_filterbank(x: torch.Tensor, fb: Filterbank, data_format):
     if not x.is_cuda:
         raise N.KapreNativeError('apply_filterbank needs a CUDA tensor')
@@ -276,6 +321,7 @@ def apply_filterbank(x: torch.Tensor, fb: Filterbank, data_format):
     return out
 
 
+@_device_of_first_arg
 def magnitude(x: torch.Tensor):
     if not x.is_cuda:
         raise N.KapreNativeError('magnitude needs a CUDA tensor')
@@ -288,6 +334,7 @@ def magnitude(x: torch.Tensor):
     return out
 
 
+@_device_of_first_arg
 def phase(x: torch.Tensor):
     if not x.is_cuda:
         raise N.KapreNativeError('phase needs a CUDA tensor')
@@ -298,6 +345,7 @@ def phase(x: torch.Tensor):
     return out
 
 
+@_device_of_first_arg
 def magnitude_to_decibel(x, ref_value=1.0, amin=1e-5, dynamic_range=80.0):
     t, was_host = to_device(x, torch.float32)
     t = t.contiguous()
@@ -318,6 +366,7 @@ def magnitude_to_decibel(x, ref_value=1.0, amin=1e-5, dynamic_range=80.0):
 _PAD_MODES = {'symmetric': 0, 'reflect': 1, 'constant': 2}
 
 
+@_device_of_first_arg
 def delta(x: torch.Tensor, win_length: int, mode: str, data_format: str):
     """kapre.Delta along the time axis of (b, t, f, ch) / (b, ch, t, f)."""
     if not x.is_cuda:
@@ -340,6 +389,7 @@ def _frames_for(length, frame_length, hop, pad_end):
     return -(-length // hop) if pad_end else max(0, 1 + (length - frame_length) // hop)
 
 
+@_device_of_first_arg
 def frame(x: torch.Tensor, frame_length, hop_length, pad_end, pad_value, data_format):
     """kapre.Frame: (b, t, ch) -> (b, frames, frame_length, ch) or (b, ch, t) -> (b, ch, frames, frame_length)."""
     if not x.is_cuda:
@@ -354,6 +404,7 @@ def frame(x: torch.Tensor, frame_length, hop_length, pad_end, pad_value, data_fo
     return out
 
 
+@_device_of_first_arg
 def energy(x: torch.Tensor, frame_length, hop_length, pad_end, pad_value, scale, data_format):
     """kapre.Energy: scale * sum of squares per frame; (b, t, ch) -> (b, frames, ch), (b, ch, t) -> (b, ch, frames)."""
     if not x.is_cuda:

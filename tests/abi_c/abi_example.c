@@ -57,8 +57,8 @@ int main(int argc, char** argv) {
     CK(cudaStreamCreate(&st));
     CK(cudaMalloc((void**)&x_dev, (size_t)B * L * sizeof(float)));
     CK(cudaMalloc((void**)&y_dev, (size_t)B * T * n_mels * sizeof(float)));
-    CK(cudaMalloc(&ws_dev, (size_t)B * 4));
-    CK(cudaMemsetAsync(ws_dev, 0, (size_t)B * 4, st));                     /* once: the workspace is self-cleaning */
+    CK(cudaMalloc(&ws_dev, (size_t)B * 8));
+    CK(cudaMemsetAsync(ws_dev, 0, (size_t)B * 8, st));                     /* once: the workspace is self-cleaning */
     CK(cudaMemcpyAsync(x_dev, wave, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
 
     /* mono (batch, length) waveform -> (batch, frames, mel) spectrogram, described by element strides */

@@ -226,6 +226,38 @@ def test_stft_magnitude_db_and_clamp(K, fmt):
     assert np.abs(got - ref).max() < 5e-3
 
 
+def test_decibel_clamp_long_items_nan_and_workspace_reuse(K):
+    """The clamp pass runs several CTAs per long item (here 3 and 2 chunks), keeps the workspace self-cleaning across
+    calls of different batch sizes, and an item that contains a NaN comes out all-NaN while its neighbours are untouched
+    (tf.maximum / tf.reduce_max propagate NaN, kapre/backend.py:186-192)."""
+    rng = np.random.default_rng(5)
+    L = 16000 * 4
+    t = np.arange(L) / 16000.0
+    kw = dict(n_fft=2048, hop_length=512, return_decibel=True, db_dynamic_range=50.0, input_data_format='channels_first',
+              output_data_format='channels_first')
+    layer = K.get_stft_magnitude_layer(**kw)
+    for B in (3, 1, 4):                          # item = 122 frames x 1025 bins = 125 050 values -> 4 chunks
+        x = (1e-3 * rng.uniform(-1, 1, size=(B, 1, L))).astype(np.float32)
+        x[0, 0] += np.sin(2 * np.pi * 440.0 * t)                  # loud tone: the clamp binds in item 0
+        got = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+        ref = O.stft_magnitude_layer(x, **kw)
+        assert (np.abs(ref - O.stft_magnitude_layer(x, **dict(kw, db_dynamic_range=1e9))) > 1.0).any()
+        assert np.abs(got - ref).max() < 5e-3
+    # fused log-mel and the stand-alone layer: NaN in one item
+    x = rng.uniform(-1, 1, size=(3, 1, 9000)).astype(np.float32)
+    x[1, 0, 4321] = np.nan
+    mel = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, n_mels=64, return_decibel=True,
+                                     input_data_format='channels_first', output_data_format='channels_first')
+    y = mel(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.isnan(y[1]).all() and np.isfinite(y[0]).all() and np.isfinite(y[2]).all()
+    y2 = mel(torch.from_numpy(np.nan_to_num(x)).cuda()).cpu().numpy()         # the workspace was left clean
+    assert np.isfinite(y2).all() and np.array_equal(y2[0], y[0])
+    m = np.abs(rng.normal(size=(3, 40, 33))).astype(np.float32)
+    m[2, 7, 5] = np.nan
+    d = K.backend.magnitude_to_decibel(m)
+    assert np.isnan(d[2]).all() and np.isfinite(d[:2]).all()
+
+
 @pytest.mark.parametrize('dynamic_range', [80.0, 120.0])
 def test_magnitude_to_decibel_literal(K, golden, dynamic_range):
     """Mirror of tests/test_backend.py:15-40 (per-row maximum)."""
