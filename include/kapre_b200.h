@@ -164,6 +164,9 @@ int kapre_profile_read(double* total_ms, uint64_t* launches);
  * n_fft = 1024 / hop = 256 real FFT as a tcgen05 (5th-gen tensor core) GEMM with TMEM accumulators, fp32-grade via
  * the 3xTF32 split.  Layout of `out_dev` and the meaning of `store` are documented at the definition
  * (kapre_b200/csrc/kapre_b200.cu) and in DESIGN.md. */
+/* Experimental: the next tensor-core (KAPRE_B200_TC=1) fused launch also writes its complex spectrum, (signals, frames, 513)
+ * complex64, to dbg_dev -- used by the parity tests of the tcgen05 FFT stages. */
+int kapre_tc_set_debug(void* dbg_dev);
 int kapre_tc_dft_stage1(const float* x_dev, int n_items, long long item_stride, int length, float* out_dev, int store,
                         int* grid_out, const float* fmat_override_dev, void* stream);
 

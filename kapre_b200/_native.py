@@ -61,6 +61,7 @@ SYMBOLS = [
     ('kapre_last_launch_info', c_char_p, []),
     ('kapre_profile_enable', c_int, [c_int]),
     ('kapre_profile_read', c_int, [POINTER(ctypes.c_double), POINTER(c_uint64)]),
+    ('kapre_tc_set_debug', c_int, [c_void_p]),
     ('kapre_tc_dft_stage1', c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, POINTER(c_int), c_void_p, c_void_p]),
 ]
 

@@ -21,6 +21,7 @@
 #include "aux_core.cuh"
 #include "mr_core.cuh"
 #include "tc_dft.cuh"
+#include "tc_mel.cuh"
 
 // ------------------------------------------------------------------------------------------
 // error handling
@@ -322,7 +323,57 @@ struct kapre_stft_plan {
     float* w = nullptr;       // generic path: window[0, win_eff)
     float2* tw = nullptr;     // generic path: exp(-2 pi i r / n_fft)
     int win_eff;
+    // tensor-core path (tc_mel.cuh; n_fft = win_length = 1024, cosine-sum window a - b cos): constant operands
+    double win_a = 0.0, win_b = 0.0;
+    float* tc_f1 = nullptr;   // stage-1 matrix hi/lo
+    float* tc_cs = nullptr;   // stage-2 C / S matrices hi/lo
+    float2* tc_tw = nullptr;  // a e^{-2 pi i n2 k1 / 1024}
+    float2* tc_w32 = nullptr; // e^{-2 pi i j / 32}
 };
+
+// (K = 32 rows, N = 32 columns) matrix -> the K-major interleaved (8 kchunk, 32 col, 4) layout of the UMMA B operand
+static void kb_tc_pack_b(const double* M, float* hi, float* lo) {
+    for (int kc = 0; kc < 8; ++kc)
+        for (int c = 0; c < 32; ++c)
+            for (int e = 0; e < 4; ++e) {
+                const float w = (float)M[(4 * kc + e) * 32 + c], h = kb_tf32_hi(w);
+                hi[(kc * 32 + c) * 4 + e] = h;
+                lo[(kc * 32 + c) * 4 + e] = w - h;
+            }
+}
+
+static int kb_tc_tables(kapre_stft_plan* p) {
+    std::vector<double> M(1024);
+    std::vector<float> f1(2048), cs(4096);
+    for (int n1 = 0; n1 < 32; ++n1)
+        for (int c = 0; c < 32; ++c) {
+            const int k1 = c >> 1;
+            const double a = -2.0 * M_PI * (double)((n1 * k1) % 32) / 32.0;
+            M[n1 * 32 + c] = (c == 1) ? ((n1 & 1) ? -1.0 : 1.0) : ((c & 1) ? sin(a) : cos(a));
+        }
+    kb_tc_pack_b(M.data(), f1.data(), f1.data() + 1024);
+    for (int n2 = 0; n2 < 32; ++n2)
+        for (int k2 = 0; k2 < 32; ++k2) M[n2 * 32 + k2] = cos(2.0 * M_PI * (double)((n2 * k2) % 32) / 32.0);
+    kb_tc_pack_b(M.data(), cs.data(), cs.data() + 1024);
+    for (int n2 = 0; n2 < 32; ++n2)
+        for (int k2 = 0; k2 < 32; ++k2) M[n2 * 32 + k2] = sin(2.0 * M_PI * (double)((n2 * k2) % 32) / 32.0);
+    kb_tc_pack_b(M.data(), cs.data() + 2048, cs.data() + 3072);
+    std::vector<float2> tw(18 * 32), w32(16);
+    for (int k1 = 0; k1 < 18; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const double a = -2.0 * M_PI * (double)(n2 * k1) / 1024.0;
+            tw[k1 * 32 + n2] = make_float2((float)(p->win_a * cos(a)), (float)(p->win_a * sin(a)));
+        }
+    for (int j = 0; j < 16; ++j) {
+        const double a = -2.0 * M_PI * (double)j / 32.0;
+        w32[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    int rc;
+    if ((rc = kb_upload(f1, &p->tc_f1)) || (rc = kb_upload(cs, &p->tc_cs)) || (rc = kb_upload(tw, &p->tc_tw)) ||
+        (rc = kb_upload(w32, &p->tc_w32)))
+        return rc;
+    return 0;
+}
 
 struct kapre_istft_plan {
     int n_fft, win_length, hop, Q, win;
@@ -350,6 +401,8 @@ struct kapre_filterbank {
     int* mg = nullptr;
 };
 
+static float2* g_tc_dbg = nullptr;   // experimental: complex-spectrum dump of the next tensor-core launch (kapre_tc_set_debug)
+
 static int kb_env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -361,6 +414,9 @@ static int kb_env_int(const char* name, int dflt) {
 struct FwdCfg { int TF, NW, smem, bps; };
 #ifndef KB_FBMMA_DEFAULT
 #define KB_FBMMA_DEFAULT 0
+#endif
+#ifndef KB_TC_DEFAULT
+#define KB_TC_DEFAULT 0
 #endif
 
 // Tile shape of the fused forward kernel.  Measured on B200 (profiles/): the kernel is
@@ -711,6 +767,10 @@ int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const floa
             p->cosw = 1;
             p->cw_a0 = (float)(0.5 * ca);
         }
+        if (n_fft == 1024 && win_length == 1024 && kb_fit_cosine_window(window_host, win_length, n_fft, &ca, &cb) && ca > 0.0) {
+            p->win_a = ca; p->win_b = cb;
+            if ((rc = kb_tc_tables(p))) { kapre_stft_plan_destroy(p); return rc; }
+        }
     }
     {   // generic tables are always built: they also serve sizes the fused kernel cannot take
         std::vector<float> w(window_host, window_host + p->win_eff);
@@ -728,6 +788,7 @@ int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const floa
 void kapre_stft_plan_destroy(kapre_stft_plan* p) {
     if (!p) return;
     cudaFree(p->wh); cudaFree(p->cwq); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->w); cudaFree(p->tw);
+    cudaFree(p->tc_f1); cudaFree(p->tc_cs); cudaFree(p->tc_tw); cudaFree(p->tc_w32);
     delete p;
 }
 
@@ -854,6 +915,46 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
                               (long long)(Ln - 1) * xd->stride_l;
     const bool bulk = (xd->stride_l == 1) && (((uintptr_t)x_dev & 3) == 0) && xd->stride_b >= 0 && xd->stride_c >= 0 &&
                       kb_env_int("KAPRE_B200_NOBULK", 0) == 0;
+    // ---- tensor-core FFT path (tc_mel.cuh): n_fft = win_length = 1024, cosine-sum window, hop 128 / 256, planar signals ----
+    if (fbmode && plan->tc_f1 && (plan->hop == 256 || plan->hop == 128) && xd->stride_l == 1 && fb->n_bands <= 128 &&
+        fb->cw && kb_env_int("KAPRE_B200_TC", KB_TC_DEFAULT)) {
+        const KbTcMelSmem TL = kb_tcm_smem_layout(fb->n_chunks);
+        if (TL.total <= plan->dev.smem_optin) {
+            KbTcMelParams q{};
+            q.x = x_dev; q.x_sb = xd->stride_b; q.x_sc = xd->stride_c;
+            q.B = B; q.C = C; q.L = Ln; q.T = T; q.hop = plan->hop; q.pad_left = pad_left;
+            q.wc = (float)(plan->win_b / (2.0 * plan->win_a));
+            q.f1 = plan->tc_f1; q.cs = plan->tc_cs; q.tw = plan->tc_tw; q.w32 = plan->tc_w32;
+            q.cw = fb->cw; q.cm = fb->cm; q.cg = fb->cg; q.n_chunks = fb->n_chunks; q.n_bands = fb->n_bands;
+            q.out = (float*)out_dev; q.o_sb = od->stride_b; q.o_sc = od->stride_c; q.o_st = od->stride_t; q.o_sk = od->stride_f;
+            q.db = dbmode ? 1 : 0;
+            if (dbmode) { q.amin = db->amin; q.db_mul = db_mul; q.db_sub = db_sub; q.item_max = (unsigned int*)workspace_dev; }
+            q.dbg = g_tc_dbg; g_tc_dbg = nullptr;
+            q.n_tiles_t = (T + TCM_TF - 1) / TCM_TF;
+            const long long tiles = (long long)B * C * q.n_tiles_t;
+            if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
+            const int grid = (int)(tiles < plan->dev.sm_count ? tiles : plan->dev.sm_count);
+            if ((rc = kb_set_smem(kb_tc_mel_kernel, TL.total))) return rc;
+            {
+                KbProfScope prof(st);
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TCM_THREADS); lc.dynamicSmemBytes = (size_t)TL.total; lc.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                lc.attrs = attr; lc.numAttrs = kb_env_int("KAPRE_B200_PDL_FWD", 1) ? 1 : 0;
+                KB_CUDA(cudaLaunchKernelEx(&lc, kb_tc_mel_kernel, q));
+                g_launches++;
+            }
+            char buf[160];
+            snprintf(buf, sizeof(buf), "TC tcgen05 n_fft1024 hop%d grid%d smem%d tiles%lld", plan->hop, grid, TL.total, tiles);
+            g_launch_info = buf;
+            if (dbmode)
+                rc = kb_launch_clamp((float*)out_dev, B, db_item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
+                                     db->dynamic_range, st, db_run, db_period);
+            return rc;
+        }
+    }
     FwdCfg cfg;
     // filterbank phase on the tensor pipe (mma.sync 3xTF32) or on the CUDA cores (chunk lists)
     const int fbmma = (fbmode && fb->mw && kb_env_int("KAPRE_B200_FBMMA", KB_FBMMA_DEFAULT)) ? 1 : 0;
@@ -1250,6 +1351,9 @@ int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_ite
     return kb_launch_clamp(out_dev, n_items, item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
                            db->dynamic_range, st);
 }
+
+// Experimental: the next tensor-core log-mel launch also dumps its complex spectrum (signals, T, 513) float2 to dbg_dev.
+int kapre_tc_set_debug(void* dbg_dev) { g_tc_dbg = (float2*)dbg_dev; return 0; }
 
 // ---- experimental: tensor-core (tcgen05) DFT stage, see tc_dft.cuh -----------------------------------
 // Stage 1 of the 32 x 32 factorisation of the n_fft = 1024 / hop = 256 real FFT over `n_items` waveforms of

@@ -1,0 +1,423 @@
+// Fused log-mel kernel with the real FFT on the 5th-generation tensor cores (tcgen05 + TMEM), n_fft = 1024.
+//
+// Replaces the same reference chain as stft_core.cuh (kapre/time_frequency.py:164-187 STFT, :351-359 |.|,
+// :535-548 filterbank, kapre/backend.py:186-188 decibel) for the headline configuration: n_fft = win_length = 1024,
+// a cosine-sum window (tf.signal.hann_window -- kapre's default -- or hamming_window), hop 128 or 256.
+//
+// 1024 = 32 x 32 Cooley-Tukey, n = 32 n1 + n2, k = k1 + 32 k2, both stages as fp32-grade GEMMs (3xTF32 split,
+// fp32 accumulators in TMEM):
+//   stage 1 (tc_dft.cuh)  S[(f, n2), k1] = sum_n1 x[hop f + 32 n1 + n2] e^{-2 pi i n1 k1 / 32}: A = the RAW hop-overlapped
+//            sample buffer read in place as an MN-major SWIZZLE_128B_BASE32B operand, M = 4 frames x 32, K = 32, N = 32
+//            (k1 = 0..15 as (Re, Im); the zero Im(k1 = 0) column carries the real k1 = 16).
+//   between  one thread per row (f, n2):  U[k1] = a w^k1 S[k1]  (w = e^{-2 pi i n2 / 1024}, table);  the WINDOW
+//            a - b cos(2 pi n / N) is a 3-tap filter along k1 of the twiddled values: T[k1] = U[k1] - b/(2a) (U[k1-1] + U[k1+1])
+//            (U[-1] = conj U[1], U[17] = a w^17 conj S[15]) -- so the samples are never windowed in the time domain and
+//            every sample is split into TF32 hi/lo once, not once per overlapping frame.  T (k1 = 1..16) is split
+//            and stored as the MN-major A operand of stage 2 (the transpose between the stages is free: a row of
+//            stage 1 is a K row of stage 2).  k1 = 0 is a REAL sequence: its 32-point DFT over n2 (bins 0, 32, .., 512)
+//            is done with warp shuffles.
+//   stage 2  X[k1 + 32 k2] = sum_n2 T[n2, k1] e^{-2 pi i n2 k2 / 32}: rows (f, k1) M = 8 frames x 16, K = 32, as four
+//            real products D_re = A_re C + A_im S, D_im = A_im C - A_re S (N = 32 each; the minus through the
+//            instruction descriptor's negate-A bit).  Thread (f, k1) then holds bins k1 + 32 k2 (k2 < 16) and, through
+//            conjugate symmetry, 1024 - (k1 + 32 k2) (k2 >= 16): magnitudes straight from registers.
+//   mel + dB  banded filterbank from the chunk lists of kb_make_fb_chunks on the CUDA cores, decibel and the per-item
+//            maximum as in stft_core.cuh.
+//
+// One CTA of 16 warps per SM, two roles: warps 0-7 (X) stage samples, issue every tcgen05.mma, and run the
+// between-stages step; warps 8-15 (Y) turn stage-2 accumulators into magnitudes, mel bands, decibels and stores.
+// The roles meet through mbarriers (tcgen05.commit for MMA completion) so that the tensor pipe, the X warps and the
+// Y warps work on three different 8-frame units at the same time.  TMEM: 2 x 64 columns stage 1, 2 x 64 stage 2.
+#pragma once
+#include "tc_dft.cuh"
+#include "stft_core.cuh"
+
+#define TCM_UNIT 8                   // frames per unit (one stage-2 GEMM tile: 8 frames x 16 k1 = 128 rows)
+#define TCM_TF 16                    // frames per tile (two units share one sample staging)
+#define TCM_XT 256                   // threads per role
+#define TCM_THREADS 512
+#define TCM_MAXROWS 152              // 128-byte sample rows per tile at hop 256: 15 * 8 + 32
+#define TCM_MS 516                   // floats per frame in the magnitude buffer (513 bins + 3 pad)
+#define TCM_MP 129                   // floats per frame in the band buffer
+
+struct KbTcMelParams {
+    const float* x;                  // waveform, strides (batch, channel), sample stride 1
+    long long x_sb, x_sc;
+    int B, C, L, T, hop, pad_left;
+    float wc;                        // b / (2 a) of the window a - b cos(2 pi n / 1024)
+    const float* f1;                 // stage-1 matrix, (hi|lo, 8 kchunk, 32 col, 4)
+    const float* cs;                 // stage-2 matrices C_hi, C_lo, S_hi, S_lo, each (8 kchunk, 32 col, 4)
+    const float2* tw;                // [18][32]: a e^{-2 pi i n2 k1 / 1024}, k1 = 0..17
+    const float2* w32;               // [16]: e^{-2 pi i j / 32}
+    const kb_f4* cw;                 // filterbank chunk lists (kb_make_fb_chunks, 32 groups)
+    const kb_i2* cm;
+    const int* cg;
+    int n_chunks, n_bands;
+    float* out;                      // (batch, channel, frame, band) element strides
+    long long o_sb, o_sc, o_st, o_sk;
+    int db;                          // 1: decibel output + per-item maximum
+    float amin, db_mul, db_sub;
+    unsigned int* item_max;
+    float2* dbg;                     // optional: complex spectrum (B*C, T, 513), debugging only
+    int n_tiles_t;                   // ceil(T / TCM_TF)
+};
+
+struct KbTcMelSmem { int hi, lo, a2, f1, cs, tw, w32, mag, outs, mag0, cw, cm, cg, bar, total; };
+KB_HD KbTcMelSmem kb_tcm_smem_layout(int n_chunks) {
+    KbTcMelSmem s;
+    int off = 0;
+    s.hi = off; off += TCM_MAXROWS * 128;                  // 19456 = 19 * 1024
+    s.lo = off; off += TCM_MAXROWS * 128;
+    s.a2 = off; off += 4 * 16384;                          // A_re hi/lo, A_im hi/lo: 4 groups x 32 rows x 128 B each
+    s.f1 = off; off += 8192;
+    s.cs = off; off += 16384;
+    s.tw = off; off += 18 * 32 * 8;
+    s.w32 = off; off += 16 * 8;
+    s.mag = off; off += TCM_UNIT * TCM_MS * 4;
+    s.outs = off; off += ((TCM_UNIT * TCM_MP * 4 + 15) & ~15);
+    s.mag0 = off; off += 2 * TCM_UNIT * 20 * 4;            // [slot][frame][17 -> 20]
+    s.cw = off; off += n_chunks * 16;
+    s.cm = off; off += ((n_chunks * 8 + 15) & ~15);
+    s.cg = off; off += 36 * 4;
+    s.bar = off; off += 128;
+    s.total = off + 1024;                                  // + alignment slack
+    return s;
+}
+
+#if defined(__CUDACC__)
+namespace kbtc {
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void role_sync(int id) {          // named barrier of one 256-thread role
+    asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ int brev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
+
+}  // namespace kbtc
+
+__global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_constant__ KbTcMelParams p) {
+    using namespace kbtc;
+    extern __shared__ char kb_tcm_raw[];
+    const uint32_t raw = smem_u32(kb_tcm_raw);
+    char* sm = kb_tcm_raw + (((raw + 1023u) & ~1023u) - raw);
+    const KbTcMelSmem L = kb_tcm_smem_layout(p.n_chunks);
+    char* hi_s = sm + L.hi;
+    char* lo_s = sm + L.lo;
+    char* a2_s = sm + L.a2;
+    float* f1_s = reinterpret_cast<float*>(sm + L.f1);
+    float* cs_s = reinterpret_cast<float*>(sm + L.cs);
+    cpx* tw_s = reinterpret_cast<cpx*>(sm + L.tw);
+    cpx* w32_s = reinterpret_cast<cpx*>(sm + L.w32);
+    float* mag_s = reinterpret_cast<float*>(sm + L.mag);
+    float* out_s = reinterpret_cast<float*>(sm + L.outs);
+    float* mag0_s = reinterpret_cast<float*>(sm + L.mag0);
+    kb_f4* cw_s = reinterpret_cast<kb_f4*>(sm + L.cw);
+    kb_i2* cm_s = reinterpret_cast<kb_i2*>(sm + L.cm);
+    int* cg_s = reinterpret_cast<int*>(sm + L.cg);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bar);     // s1_done[2], s2_done[2], d2_free[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bar + 64);
+    uint64_t* s1_done = bars;
+    uint64_t* s2_done = bars + 2;
+    uint64_t* d2_free = bars + 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time: constant tables, barriers, TMEM (256 columns) -------------------------------------------------
+    for (int i = tid; i < 2048; i += TCM_THREADS) f1_s[i] = p.f1[i];
+    for (int i = tid; i < 4096; i += TCM_THREADS) cs_s[i] = p.cs[i];
+    for (int i = tid; i < 18 * 32; i += TCM_THREADS) { const float2 t = p.tw[i]; tw_s[i] = cmake(t.x, t.y); }
+    for (int i = tid; i < 16; i += TCM_THREADS) { const float2 t = p.w32[i]; w32_s[i] = cmake(t.x, t.y); }
+    for (int i = tid; i < p.n_chunks; i += TCM_THREADS) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
+    for (int i = tid; i <= 32; i += TCM_THREADS) cg_s[i] = p.cg[i];
+    for (int i = tid; i < TCM_UNIT * TCM_MS; i += TCM_THREADS) mag_s[i] = 0.0f;     // incl. the pad bins, never written again
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) bar_init(bars + i, 1);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // PDL: everything above touched constants only
+    asm volatile("griddepcontrol.launch_dependents;");
+    const uint32_t tmem = *tmem_slot;
+    const int n_tiles = p.B * p.C * p.n_tiles_t;
+    const int hop_rows = p.hop >> 5;
+    const int tile_rows = (TCM_TF - 1) * hop_rows + 32;
+
+    if (warp < 8) {
+        // =========================================== role X ===========================================================
+        const uint32_t idesc1 = make_idesc_tf32(128, 32, 1, 0);
+        const uint32_t idesc2 = idesc1;                      // stage 2 has the same shape / majors
+        const uint32_t idesc2n = idesc1 | (1u << 13);        // negate A
+        const uint32_t a_hi = smem_u32(hi_s), a_lo = smem_u32(lo_s);
+        const uint32_t f_hi = smem_u32(f1_s), f_lo = f_hi + 4096;
+        const uint32_t a2 = smem_u32(a2_s);
+        const uint32_t c_hi = smem_u32(cs_s), c_lo = c_hi + 4096, s_hi = c_hi + 8192, s_lo = c_hi + 12288;
+        const uint32_t lbo1 = (uint32_t)p.hop * 4u;
+
+        // stage 1 of unit `uu` (0 / 1) of the staged tile into D1 slot uu
+        auto issue_s1 = [&](int uu) {
+#pragma unroll 1
+            for (int mt = 0; mt < 2; ++mt) {
+                const uint32_t d = tmem + (uint32_t)(uu * 64 + mt * 32);
+                const uint32_t row0 = (uint32_t)((uu * TCM_UNIT + mt * 4) * hop_rows);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t aoff = (row0 + 8u * j) * 128u;
+                    const uint64_t dah = make_desc(a_hi + aoff, lbo1, 512, 1), dal = make_desc(a_lo + aoff, lbo1, 512, 1);
+                    const uint64_t dbh = make_desc(f_hi + (uint32_t)(j * 1024), 512, 128, 0);
+                    const uint64_t dbl = make_desc(f_lo + (uint32_t)(j * 1024), 512, 128, 0);
+                    mma_tf32(d, dal, dbh, idesc1, acc); acc = 1;
+                    mma_tf32(d, dah, dbl, idesc1, 1);
+                    mma_tf32(d, dah, dbh, idesc1, 1);
+                }
+            }
+            mma_commit(s1_done + uu);
+        };
+        // stage 2 of the unit whose A operand sits in a2_s into D2 slot uu
+        auto issue_s2 = [&](int uu) {
+            const uint32_t dre = tmem + (uint32_t)(128 + uu * 64), dim = dre + 32;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t ko = (uint32_t)(j * 1024);
+                const uint64_t rh = make_desc(a2 + 0 * 16384 + ko, 4096, 512, 1), rl = make_desc(a2 + 1 * 16384 + ko, 4096, 512, 1);
+                const uint64_t ih = make_desc(a2 + 2 * 16384 + ko, 4096, 512, 1), il = make_desc(a2 + 3 * 16384 + ko, 4096, 512, 1);
+                const uint64_t ch = make_desc(c_hi + ko, 512, 128, 0), cl = make_desc(c_lo + ko, 512, 128, 0);
+                const uint64_t sh = make_desc(s_hi + ko, 512, 128, 0), sl = make_desc(s_lo + ko, 512, 128, 0);
+                // D_re += A_re C + A_im S
+                mma_tf32(dre, rl, ch, idesc2, acc);
+                mma_tf32(dre, rh, cl, idesc2, 1);
+                mma_tf32(dre, rh, ch, idesc2, 1);
+                mma_tf32(dre, il, sh, idesc2, 1);
+                mma_tf32(dre, ih, sl, idesc2, 1);
+                mma_tf32(dre, ih, sh, idesc2, 1);
+                // D_im += A_im C - A_re S
+                mma_tf32(dim, il, ch, idesc2, acc);
+                mma_tf32(dim, ih, cl, idesc2, 1);
+                mma_tf32(dim, ih, ch, idesc2, 1);
+                mma_tf32(dim, rl, sh, idesc2n, 1);
+                mma_tf32(dim, rh, sl, idesc2n, 1);
+                mma_tf32(dim, rh, sh, idesc2n, 1);
+                acc = 1;
+            }
+            mma_commit(s2_done + uu);
+        };
+        // samples of one tile: global -> (hi, lo) swizzled rows.  Element i of the tile is sample s0 + i of the signal.
+        auto stage_tile = [&](const float* xsig, long long s0) {
+            const int n = tile_rows * 32;
+            for (int i = tid; i < n; i += TCM_XT) {
+                const long long s = s0 + i;
+                const float v = (s >= 0 && s < p.L) ? __ldg(xsig + s) : 0.0f;
+                const float h = tf32_hi(v);
+                const uint32_t o = swz((uint32_t)i >> 5, (uint32_t)i & 31u);
+                *reinterpret_cast<float*>(hi_s + o) = h;
+                *reinterpret_cast<float*>(lo_s + o) = v - h;
+            }
+        };
+
+        int k = 0;                                              // this CTA's tile counter
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int sig = tile / p.n_tiles_t;
+            const int tt = tile - sig * p.n_tiles_t;
+            const int b = sig / p.C, c = sig - b * p.C;
+            const int t0 = tt * TCM_TF;
+            const float* xsig = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc;
+            // Sample buffers are free: E1 of both units of the previous tile waited for their stage-1 GEMMs.
+            stage_tile(xsig, (long long)t0 * p.hop - p.pad_left);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            role_sync(1);
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue_s1(0);
+                issue_s1(1);
+            }
+            for (int uu = 0; uu < 2; ++uu) {
+                bar_wait(s1_done + uu, (uint32_t)(k & 1));
+                // A2 is free once stage 2 of the previous unit has completed
+                if (uu == 1) bar_wait(s2_done + 0, (uint32_t)(k & 1));
+                else if (k > 0) bar_wait(s2_done + 1, (uint32_t)((k - 1) & 1));
+                // D2 slot uu and mag0 slot uu are free once Y has read unit uu of the previous tile
+                if (k > 0) bar_wait(d2_free + uu, (uint32_t)((k - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+                // ---- between the stages: one thread per row (frame = warp, n2 = lane) ------------------------------
+                {
+                    const int n2 = lane, fl = warp;             // frame in unit
+                    uint32_t sv[32];
+                    tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(uu * 64 + (warp >> 2) * 32), sv);
+                    const float S0 = __uint_as_float(sv[0]), S16 = __uint_as_float(sv[1]);
+                    const float wc = p.wc;
+                    const cpx t0w = tw_s[0 * 32 + n2];
+                    const cpx U0 = cmake(t0w.re * S0, 0.0f);
+                    cpx Uc = cmul(cmake(__uint_as_float(sv[2]), __uint_as_float(sv[3])), tw_s[1 * 32 + n2]);
+                    const float T0 = U0.re - 2.0f * wc * Uc.re;   // k1 = 0: real (U[-1] = conj U[1])
+                    cpx Um = U0;
+                    float tre[16], tim[16];
+#pragma unroll
+                    for (int k1 = 1; k1 <= 16; ++k1) {
+                        cpx Sn;
+                        if (k1 < 15) Sn = cmake(__uint_as_float(sv[2 * (k1 + 1)]), __uint_as_float(sv[2 * (k1 + 1) + 1]));
+                        else if (k1 == 15) Sn = cmake(S16, 0.0f);
+                        else Sn = cmake(__uint_as_float(sv[30]), -__uint_as_float(sv[31]));   // S[17] = conj S[15]
+                        const cpx Up = cmul(Sn, tw_s[(k1 + 1) * 32 + n2]);
+                        const cpx T = cfma_s(cadd(Um, Up), -wc, Uc);
+                        tre[k1 - 1] = T.re; tim[k1 - 1] = T.im;
+                        Um = Uc; Uc = Up;
+                    }
+                    // A operand of stage 2: rows n2, M-group = frame pair, 16 consecutive floats per frame
+                    {
+                        const uint32_t rowb = (uint32_t)((fl >> 1) * 4096 + n2 * 128);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t unit = (uint32_t)((fl & 1) * 2 + (i >> 1));
+                            const uint32_t o = rowb + (((unit ^ ((uint32_t)n2 & 3u)) << 5) | (uint32_t)((i & 1) << 4));
+                            float4 rh, rl, ih, il;
+                            rh.x = tf32_hi(tre[4 * i]); rh.y = tf32_hi(tre[4 * i + 1]); rh.z = tf32_hi(tre[4 * i + 2]); rh.w = tf32_hi(tre[4 * i + 3]);
+                            rl.x = tre[4 * i] - rh.x; rl.y = tre[4 * i + 1] - rh.y; rl.z = tre[4 * i + 2] - rh.z; rl.w = tre[4 * i + 3] - rh.w;
+                            ih.x = tf32_hi(tim[4 * i]); ih.y = tf32_hi(tim[4 * i + 1]); ih.z = tf32_hi(tim[4 * i + 2]); ih.w = tf32_hi(tim[4 * i + 3]);
+                            il.x = tim[4 * i] - ih.x; il.y = tim[4 * i + 1] - ih.y; il.z = tim[4 * i + 2] - ih.z; il.w = tim[4 * i + 3] - ih.w;
+                            *reinterpret_cast<float4*>(a2_s + 0 * 16384 + o) = rh;
+                            *reinterpret_cast<float4*>(a2_s + 1 * 16384 + o) = rl;
+                            *reinterpret_cast<float4*>(a2_s + 2 * 16384 + o) = ih;
+                            *reinterpret_cast<float4*>(a2_s + 3 * 16384 + o) = il;
+                        }
+                    }
+                    // k1 = 0: 32-point DFT of the real sequence T0[n2] across the warp (radix-2 DIF, bit-reversed result)
+                    {
+                        cpx y = cmake(T0, 0.0f);
+#pragma unroll
+                        for (int s = 0; s < 5; ++s) {
+                            const int half = 16 >> s;
+                            cpx q;
+                            q.re = __shfl_xor_sync(0xffffffffu, y.re, half);
+                            q.im = __shfl_xor_sync(0xffffffffu, y.im, half);
+                            const cpx w = w32_s[(lane & (half - 1)) << s];
+                            y = (lane & half) ? cmul(csub(q, y), w) : cadd(y, q);
+                        }
+                        const int k2 = brev5(lane);
+                        if (k2 <= 16) {
+                            mag0_s[(uu * TCM_UNIT + fl) * 20 + k2] = kb_sqrt(cnorm(y));
+                            if (p.dbg) {
+                                const int t = t0 + uu * TCM_UNIT + fl;
+                                if (t < p.T) p.dbg[((long long)sig * p.T + t) * 513 + 32 * k2] = make_float2(y.re, y.im);
+                            }
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                role_sync(1);
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    issue_s2(uu);
+                }
+            }
+        }
+    } else {
+        // =========================================== role Y ===========================================================
+        const int ty = tid - TCM_XT, wy = warp - 8;
+        const int q = wy & 3, h = wy >> 2;
+        int k = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int sig = tile / p.n_tiles_t;
+            const int tt = tile - sig * p.n_tiles_t;
+            const int b = sig / p.C, c = sig - b * p.C;
+            const int t0 = tt * TCM_TF;
+            const long long obase = (long long)b * p.o_sb + (long long)c * p.o_sc;
+            float rmax = 0.0f;
+            for (int uu = 0; uu < 2; ++uu) {
+                bar_wait(s2_done + uu, (uint32_t)(k & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // ---- stage-2 accumulators -> magnitudes (row = (frame, k1), 16 of the 32 k2 per thread) ---------------
+                {
+                    const int fl = 2 * q + (lane >> 4), k1 = 1 + (lane & 15);
+                    uint32_t re[16], im[16];
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + uu * 64 + 16 * h);
+                    tmem_ld16(ta, re);
+                    tmem_ld16(ta + 32, im);
+                    float* mrow = mag_s + fl * TCM_MS;
+                    const int t = t0 + uu * TCM_UNIT + fl;
+                    if (!(h == 1 && k1 == 16)) {          // k1 = 16, k2 >= 16 mirrors onto the k1 = 16, k2 < 16 bins
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                            const int kk = k1 + 32 * (16 * h + j);
+                            const int bin = h ? 1024 - kk : kk;
+                            mrow[bin] = kb_sqrt(xr * xr + xi * xi);
+                            if (p.dbg && t < p.T) p.dbg[((long long)sig * p.T + t) * 513 + bin] = make_float2(xr, h ? -xi : xi);
+                        }
+                    }
+                    // bins 0, 32, .., 512 from the X role's shuffle DFT
+                    if (ty < TCM_UNIT * 17) {
+                        const int f0 = ty / 17, k2 = ty - f0 * 17;
+                        mag_s[f0 * TCM_MS + 32 * k2] = mag0_s[(uu * TCM_UNIT + f0) * 20 + k2];
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                role_sync(2);
+                if (ty == 0) bar_arrive(d2_free + uu);      // D2 slot and mag0 slot may be overwritten
+                // ---- mel filterbank: 32 lane groups x 8 frames walk the 4-bin chunk lists ----------------------------
+                {
+                    const int grp = ty >> 3, f = ty & 7;
+                    const float* mrow = mag_s + f * TCM_MS;
+                    float a0 = 0.0f, a1 = 0.0f;
+                    const int ce = cg_s[grp + 1];
+                    for (int i = cg_s[grp]; i < ce; ++i) {
+                        const kb_f4 wv = cw_s[i];
+                        const kb_i2 mt = cm_s[i];
+                        const float2 m01 = *reinterpret_cast<const float2*>(mrow + mt.x);
+                        const float2 m23 = *reinterpret_cast<const float2*>(mrow + mt.x + 2);
+                        a0 += wv.x * m01.x; a1 += wv.y * m01.y;
+                        a0 += wv.z * m23.x; a1 += wv.w * m23.y;
+                        if (mt.y >= 0) { out_s[f * TCM_MP + mt.y] = a0 + a1; a0 = 0.0f; a1 = 0.0f; }
+                    }
+                }
+                role_sync(2);
+                // ---- decibel + coalesced store: warp = frame ----------------------------------------------------------
+                {
+                    const int t = t0 + uu * TCM_UNIT + wy;
+                    if (t < p.T) {
+                        float* orow = p.out + obase + (long long)t * p.o_st;
+                        const float* srow = out_s + wy * TCM_MP;
+                        for (int m = lane; m < p.n_bands; m += 32) {
+                            float v = srow[m];
+                            if (p.db) {
+                                v = kb_floor_keepnan(v, p.amin);
+                                rmax = kb_max_keepnan(rmax, v);
+                                v = p.db_mul * kb_log2(v) - p.db_sub;
+                            }
+                            orow[(long long)m * p.o_sk] = v;
+                        }
+                    }
+                }
+                // next unit's magnitudes may be written now: every Y thread passed the barrier after the filterbank;
+                // out_s is rewritten only after the next role_sync
+            }
+            if (p.db) {
+                const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
+                if (lane == 0 && wm != 0u) atomicMax(p.item_max + b, wm);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    }
+}
+#endif  // __CUDACC__
