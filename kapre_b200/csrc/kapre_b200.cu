@@ -336,7 +336,7 @@ static void kb_tc_pack_b(const double* M, float* hi, float* lo) {
     for (int kc = 0; kc < 8; ++kc)
         for (int c = 0; c < 32; ++c)
             for (int e = 0; e < 4; ++e) {
-                const float w = (float)M[(4 * kc + e) * 32 + c], h = kb_tf32_hi(w);
+                const float w = (float)M[(4 * kc + e) * 32 + c], h = kb_tf32_rn(w);
                 hi[(kc * 32 + c) * 4 + e] = h;
                 lo[(kc * 32 + c) * 4 + e] = w - h;
             }
@@ -931,6 +931,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
             if (dbmode) { q.amin = db->amin; q.db_mul = db_mul; q.db_sub = db_sub; q.item_max = (unsigned int*)workspace_dev; }
             q.dbg = g_tc_dbg; g_tc_dbg = nullptr;
             q.n_tiles_t = (T + TCM_TF - 1) / TCM_TF;
+            q.ablate = kb_env_int("KAPRE_B200_TC_ABLATE", 0);
             const long long tiles = (long long)B * C * q.n_tiles_t;
             if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
             const int grid = (int)(tiles < plan->dev.sm_count ? tiles : plan->dev.sm_count);

@@ -175,6 +175,15 @@ static inline float kb_tf32_hi(float v) {
     std::memcpy(&r, &u, 4);
     return r;
 }
+// nearest TF32 value (ties away from zero, like cvt.rna.tf32.f32); v - kb_tf32_rn(v) is exact in fp32
+static inline float kb_tf32_rn(float v) {
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    u = (u + 0x1000u) & 0xffffe000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
 static inline void kb_make_fb_mma(const float* fb, int n_freq, int n_bands, std::vector<kb_f4>& mw,
                                   std::vector<kb_i2>& ms, std::vector<int>& mg) {
     struct Job { int j, s0, s1; };   // column tile, k-steps [s0, s1)

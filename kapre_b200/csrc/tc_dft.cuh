@@ -59,6 +59,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with a compile-time accumulate flag (no predicate set-up per instruction in unrolled issue loops)
+template <bool ACC>
+__device__ __forceinline__ void mma_tf32_c(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -69,6 +79,7 @@ __device__ __forceinline__ void bar_init(uint64_t* bar, int count) {
 // bounded wait: a descriptor / barrier mistake must not hang the GPU box -- trap instead
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t b = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         uint32_t ok;
         asm volatile(

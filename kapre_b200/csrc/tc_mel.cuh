@@ -23,18 +23,20 @@
 //   mel + dB  banded filterbank from the chunk lists of kb_make_fb_chunks on the CUDA cores, decibel and the per-item
 //            maximum as in stft_core.cuh.
 //
-// One CTA of 16 warps per SM, two roles: warps 0-7 (X) stage samples, issue every tcgen05.mma, and run the
-// between-stages step; warps 8-15 (Y) turn stage-2 accumulators into magnitudes, mel bands, decibels and stores.
-// The roles meet through mbarriers (tcgen05.commit for MMA completion) so that the tensor pipe, the X warps and the
-// Y warps work on three different 8-frame units at the same time.  TMEM: 2 x 64 columns stage 1, 2 x 64 stage 2.
+// One CTA of 17 warps per SM, three roles: warps 0-7 (X) stage samples (cp.async into a raw buffer, then the hi/lo
+// split) and run the between-stages step; warps 8-15 (Y) turn stage-2 accumulators into magnitudes, mel bands,
+// decibels and stores; one lane of warp 16 (M) issues every tcgen05.mma.  The roles meet only through mbarriers
+// (tcgen05.commit for MMA completion, 256-arrival barriers for "operand written" / "accumulator read"), so the
+// tensor pipe, the X warps and the Y warps work on different 8-frame units at the same time and no X thread ever
+// waits for another X thread.  TMEM: 2 x 64 columns stage 1, 2 x 64 stage 2.
 #pragma once
 #include "tc_dft.cuh"
 #include "stft_core.cuh"
 
 #define TCM_UNIT 8                   // frames per unit (one stage-2 GEMM tile: 8 frames x 16 k1 = 128 rows)
 #define TCM_TF 16                    // frames per tile (two units share one sample staging)
-#define TCM_XT 256                   // threads per role
-#define TCM_THREADS 512
+#define TCM_XT 256                   // threads per role (X, Y); warp 16 issues the MMAs
+#define TCM_THREADS 544
 #define TCM_MAXROWS 152              // 128-byte sample rows per tile at hop 256: 15 * 8 + 32
 #define TCM_MS 516                   // floats per frame in the magnitude buffer (513 bins + 3 pad)
 #define TCM_MP 129                   // floats per frame in the band buffer
@@ -59,15 +61,17 @@ struct KbTcMelParams {
     unsigned int* item_max;
     float2* dbg;                     // optional: complex spectrum (B*C, T, 513), debugging only
     int n_tiles_t;                   // ceil(T / TCM_TF)
+    int ablate;                      // timing experiments only: 1 Y skips its work, 2 X skips the between-stages math, 4 no MMAs, 8 no filterbank
 };
 
-struct KbTcMelSmem { int hi, lo, a2, f1, cs, tw, w32, mag, outs, mag0, cw, cm, cg, bar, total; };
+struct KbTcMelSmem { int hi, lo, a2, raw, f1, cs, tw, w32, mag, outs, mag0, cw, cm, cg, bar, total; };
 KB_HD KbTcMelSmem kb_tcm_smem_layout(int n_chunks) {
     KbTcMelSmem s;
     int off = 0;
     s.hi = off; off += TCM_MAXROWS * 128;                  // 19456 = 19 * 1024
     s.lo = off; off += TCM_MAXROWS * 128;
     s.a2 = off; off += 4 * 16384;                          // A_re hi/lo, A_im hi/lo: 4 groups x 32 rows x 128 B each
+    s.raw = off; off += TCM_MAXROWS * 128;                 // next tile's samples as they arrive (cp.async), linear
     s.f1 = off; off += 8192;
     s.cs = off; off += 16384;
     s.tw = off; off += 18 * 32 * 8;
@@ -102,6 +106,12 @@ __device__ __forceinline__ void role_sync(int id) {          // named barrier of
     asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
 }
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+// nearest TF32 value (cvt.rna): the remainder v - tf32_rn(v) is exact in fp32 and half the size of the truncation remainder
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ int brev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
 
 }  // namespace kbtc
@@ -115,6 +125,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
     char* hi_s = sm + L.hi;
     char* lo_s = sm + L.lo;
     char* a2_s = sm + L.a2;
+    float* raw_s = reinterpret_cast<float*>(sm + L.raw);
     float* f1_s = reinterpret_cast<float*>(sm + L.f1);
     float* cs_s = reinterpret_cast<float*>(sm + L.cs);
     cpx* tw_s = reinterpret_cast<cpx*>(sm + L.tw);
@@ -125,11 +136,17 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
     kb_f4* cw_s = reinterpret_cast<kb_f4*>(sm + L.cw);
     kb_i2* cm_s = reinterpret_cast<kb_i2*>(sm + L.cm);
     int* cg_s = reinterpret_cast<int*>(sm + L.cg);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bar);     // s1_done[2], s2_done[2], d2_free[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bar + 64);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bar + 96);
+    // MMA completion (tcgen05.commit, count 1):          s1_done[2] (stage 1 of unit 0 / 1), s2_done[2]
+    // operand written / accumulator read (count 256):    d1_free[2] (X read D1), d2_free[2] (Y read D2 + mag0),
+    //                                                    a2_ready (X wrote the stage-2 A operand), smp_ready (X staged a tile)
     uint64_t* s1_done = bars;
     uint64_t* s2_done = bars + 2;
-    uint64_t* d2_free = bars + 4;
+    uint64_t* d1_free = bars + 4;
+    uint64_t* d2_free = bars + 6;
+    uint64_t* a2_ready = bars + 8;
+    uint64_t* smp_ready = bars + 9;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time: constant tables, barriers, TMEM (256 columns) -------------------------------------------------
@@ -141,12 +158,14 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
     for (int i = tid; i <= 32; i += TCM_THREADS) cg_s[i] = p.cg[i];
     for (int i = tid; i < TCM_UNIT * TCM_MS; i += TCM_THREADS) mag_s[i] = 0.0f;     // incl. the pad bins, never written again
     if (tid == 0) {
-        for (int i = 0; i < 6; ++i) bar_init(bars + i, 1);
+        for (int i = 0; i < 4; ++i) bar_init(bars + i, 1);
+        for (int i = 4; i < 10; ++i) bar_init(bars + i, TCM_XT);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the constant operands (generic stores) -> async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -157,176 +176,265 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
     const int hop_rows = p.hop >> 5;
     const int tile_rows = (TCM_TF - 1) * hop_rows + 32;
 
-    if (warp < 8) {
-        // =========================================== role X ===========================================================
-        const uint32_t idesc1 = make_idesc_tf32(128, 32, 1, 0);
-        const uint32_t idesc2 = idesc1;                      // stage 2 has the same shape / majors
-        const uint32_t idesc2n = idesc1 | (1u << 13);        // negate A
-        const uint32_t a_hi = smem_u32(hi_s), a_lo = smem_u32(lo_s);
-        const uint32_t f_hi = smem_u32(f1_s), f_lo = f_hi + 4096;
-        const uint32_t a2 = smem_u32(a2_s);
-        const uint32_t c_hi = smem_u32(cs_s), c_lo = c_hi + 4096, s_hi = c_hi + 8192, s_lo = c_hi + 12288;
-        const uint32_t lbo1 = (uint32_t)p.hop * 4u;
-
-        // stage 1 of unit `uu` (0 / 1) of the staged tile into D1 slot uu
-        auto issue_s1 = [&](int uu) {
-#pragma unroll 1
-            for (int mt = 0; mt < 2; ++mt) {
-                const uint32_t d = tmem + (uint32_t)(uu * 64 + mt * 32);
-                const uint32_t row0 = (uint32_t)((uu * TCM_UNIT + mt * 4) * hop_rows);
-                uint32_t acc = 0;
+    if (warp == 16) {
+        // =========================================== role M: MMA issue ================================================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc_tf32(128, 32, 1, 0);
+            const uint32_t idesc2 = idesc1;                      // stage 2 has the same shape / majors
+            const uint32_t idesc2n = idesc1 | (1u << 13);        // negate A
+            const uint32_t a_hi = smem_u32(hi_s), a_lo = smem_u32(lo_s);
+            const uint32_t f_hi = smem_u32(f1_s), f_lo = f_hi + 4096;
+            const uint32_t a2 = smem_u32(a2_s);
+            const uint32_t c_hi = smem_u32(cs_s), c_lo = c_hi + 4096, s_hi = c_hi + 8192, s_lo = c_hi + 12288;
+            const uint32_t lbo1 = (uint32_t)p.hop * 4u;
+            // Descriptors are built once; inside the unrolled loops only their 14-bit start-address field (16-byte units)
+            // moves, by compile-time constants.
+            const uint64_t d_ah = make_desc(a_hi, lbo1, 512, 1), d_al = make_desc(a_lo, lbo1, 512, 1);
+            const uint64_t d_fh = make_desc(f_hi, 512, 128, 0), d_fl = make_desc(f_lo, 512, 128, 0);
+            const uint64_t d_rh = make_desc(a2 + 0 * 16384, 4096, 512, 1), d_rl = make_desc(a2 + 1 * 16384, 4096, 512, 1);
+            const uint64_t d_ih = make_desc(a2 + 2 * 16384, 4096, 512, 1), d_il = make_desc(a2 + 3 * 16384, 4096, 512, 1);
+            const uint64_t d_ch = make_desc(c_hi, 512, 128, 0), d_cl = make_desc(c_lo, 512, 128, 0);
+            const uint64_t d_sh = make_desc(s_hi, 512, 128, 0), d_sl = make_desc(s_lo, 512, 128, 0);
+            // stage 1 of unit `uu` (0 / 1) of the staged tile into D1 slot uu
+            auto issue_s1 = [&](int uu) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (p.ablate & 4) { mma_commit(s1_done + uu); return; }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint32_t d = tmem + (uint32_t)(uu * 64 + mt * 32);
+                    const uint64_t rowoff = (uint64_t)((uint32_t)((uu * TCM_UNIT + mt * 4) * hop_rows) * 8u);   // rows * 128 B / 16
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t dah = d_ah + rowoff + (uint64_t)(j * 64), dal = d_al + rowoff + (uint64_t)(j * 64);
+                        const uint64_t dbh = d_fh + (uint64_t)(j * 64), dbl = d_fl + (uint64_t)(j * 64);
+                        if (j == 0) mma_tf32_c<false>(d, dal, dbh, idesc1); else mma_tf32_c<true>(d, dal, dbh, idesc1);
+                        mma_tf32_c<true>(d, dah, dbl, idesc1);
+                        mma_tf32_c<true>(d, dah, dbh, idesc1);
+                    }
+                }
+                mma_commit(s1_done + uu);
+            };
+            // stage 2 of the unit whose A operand sits in a2_s into D2 slot uu
+            auto issue_s2 = [&](int uu) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (p.ablate & 4) { mma_commit(s2_done + uu); return; }
+                const uint32_t dre = tmem + (uint32_t)(128 + uu * 64), dim = dre + 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t aoff = (row0 + 8u * j) * 128u;
-                    const uint64_t dah = make_desc(a_hi + aoff, lbo1, 512, 1), dal = make_desc(a_lo + aoff, lbo1, 512, 1);
-                    const uint64_t dbh = make_desc(f_hi + (uint32_t)(j * 1024), 512, 128, 0);
-                    const uint64_t dbl = make_desc(f_lo + (uint32_t)(j * 1024), 512, 128, 0);
-                    mma_tf32(d, dal, dbh, idesc1, acc); acc = 1;
-                    mma_tf32(d, dah, dbl, idesc1, 1);
-                    mma_tf32(d, dah, dbh, idesc1, 1);
+                    const uint64_t ko = (uint64_t)(j * 64);
+                    const uint64_t rh = d_rh + ko, rl = d_rl + ko, ih = d_ih + ko, il = d_il + ko;
+                    const uint64_t ch = d_ch + ko, cl = d_cl + ko, sh = d_sh + ko, sl = d_sl + ko;
+                    // D_re += A_re C + A_im S
+                    if (j == 0) mma_tf32_c<false>(dre, rl, ch, idesc2); else mma_tf32_c<true>(dre, rl, ch, idesc2);
+                    mma_tf32_c<true>(dre, rh, cl, idesc2);
+                    mma_tf32_c<true>(dre, rh, ch, idesc2);
+                    mma_tf32_c<true>(dre, il, sh, idesc2);
+                    mma_tf32_c<true>(dre, ih, sl, idesc2);
+                    mma_tf32_c<true>(dre, ih, sh, idesc2);
+                    // D_im += A_im C - A_re S
+                    if (j == 0) mma_tf32_c<false>(dim, il, ch, idesc2); else mma_tf32_c<true>(dim, il, ch, idesc2);
+                    mma_tf32_c<true>(dim, ih, cl, idesc2);
+                    mma_tf32_c<true>(dim, ih, ch, idesc2);
+                    mma_tf32_c<true>(dim, rl, sh, idesc2n);
+                    mma_tf32_c<true>(dim, rh, sl, idesc2n);
+                    mma_tf32_c<true>(dim, rh, sh, idesc2n);
                 }
-            }
-            mma_commit(s1_done + uu);
-        };
-        // stage 2 of the unit whose A operand sits in a2_s into D2 slot uu
-        auto issue_s2 = [&](int uu) {
-            const uint32_t dre = tmem + (uint32_t)(128 + uu * 64), dim = dre + 32;
-            uint32_t acc = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t ko = (uint32_t)(j * 1024);
-                const uint64_t rh = make_desc(a2 + 0 * 16384 + ko, 4096, 512, 1), rl = make_desc(a2 + 1 * 16384 + ko, 4096, 512, 1);
-                const uint64_t ih = make_desc(a2 + 2 * 16384 + ko, 4096, 512, 1), il = make_desc(a2 + 3 * 16384 + ko, 4096, 512, 1);
-                const uint64_t ch = make_desc(c_hi + ko, 512, 128, 0), cl = make_desc(c_lo + ko, 512, 128, 0);
-                const uint64_t sh = make_desc(s_hi + ko, 512, 128, 0), sl = make_desc(s_lo + ko, 512, 128, 0);
-                // D_re += A_re C + A_im S
-                mma_tf32(dre, rl, ch, idesc2, acc);
-                mma_tf32(dre, rh, cl, idesc2, 1);
-                mma_tf32(dre, rh, ch, idesc2, 1);
-                mma_tf32(dre, il, sh, idesc2, 1);
-                mma_tf32(dre, ih, sl, idesc2, 1);
-                mma_tf32(dre, ih, sh, idesc2, 1);
-                // D_im += A_im C - A_re S
-                mma_tf32(dim, il, ch, idesc2, acc);
-                mma_tf32(dim, ih, cl, idesc2, 1);
-                mma_tf32(dim, ih, ch, idesc2, 1);
-                mma_tf32(dim, rl, sh, idesc2n, 1);
-                mma_tf32(dim, rh, sl, idesc2n, 1);
-                mma_tf32(dim, rh, sh, idesc2n, 1);
-                acc = 1;
-            }
-            mma_commit(s2_done + uu);
-        };
-        // samples of one tile: global -> (hi, lo) swizzled rows.  Element i of the tile is sample s0 + i of the signal.
-        auto stage_tile = [&](const float* xsig, long long s0) {
-            const int n = tile_rows * 32;
-            for (int i = tid; i < n; i += TCM_XT) {
-                const long long s = s0 + i;
-                const float v = (s >= 0 && s < p.L) ? __ldg(xsig + s) : 0.0f;
-                const float h = tf32_hi(v);
-                const uint32_t o = swz((uint32_t)i >> 5, (uint32_t)i & 31u);
-                *reinterpret_cast<float*>(hi_s + o) = h;
-                *reinterpret_cast<float*>(lo_s + o) = v - h;
-            }
-        };
-
-        int k = 0;                                              // this CTA's tile counter
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-            const int sig = tile / p.n_tiles_t;
-            const int tt = tile - sig * p.n_tiles_t;
-            const int b = sig / p.C, c = sig - b * p.C;
-            const int t0 = tt * TCM_TF;
-            const float* xsig = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc;
-            // Sample buffers are free: E1 of both units of the previous tile waited for their stage-1 GEMMs.
-            stage_tile(xsig, (long long)t0 * p.hop - p.pad_left);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            role_sync(1);
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                mma_commit(s2_done + uu);
+            };
+            int k = 0;
+            if ((int)blockIdx.x < n_tiles) {
+                bar_wait(smp_ready, 0u);
                 issue_s1(0);
                 issue_s1(1);
             }
-            for (int uu = 0; uu < 2; ++uu) {
-                bar_wait(s1_done + uu, (uint32_t)(k & 1));
-                // A2 is free once stage 2 of the previous unit has completed
-                if (uu == 1) bar_wait(s2_done + 0, (uint32_t)(k & 1));
-                else if (k > 0) bar_wait(s2_done + 1, (uint32_t)((k - 1) & 1));
-                // D2 slot uu and mag0 slot uu are free once Y has read unit uu of the previous tile
-                if (k > 0) bar_wait(d2_free + uu, (uint32_t)((k - 1) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-                // ---- between the stages: one thread per row (frame = warp, n2 = lane) ------------------------------
-                {
-                    const int n2 = lane, fl = warp;             // frame in unit
-                    uint32_t sv[32];
-                    tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(uu * 64 + (warp >> 2) * 32), sv);
-                    const float S0 = __uint_as_float(sv[0]), S16 = __uint_as_float(sv[1]);
-                    const float wc = p.wc;
-                    const cpx t0w = tw_s[0 * 32 + n2];
-                    const cpx U0 = cmake(t0w.re * S0, 0.0f);
-                    cpx Uc = cmul(cmake(__uint_as_float(sv[2]), __uint_as_float(sv[3])), tw_s[1 * 32 + n2]);
-                    const float T0 = U0.re - 2.0f * wc * Uc.re;   // k1 = 0: real (U[-1] = conj U[1])
-                    cpx Um = U0;
-                    float tre[16], tim[16];
-#pragma unroll
-                    for (int k1 = 1; k1 <= 16; ++k1) {
-                        cpx Sn;
-                        if (k1 < 15) Sn = cmake(__uint_as_float(sv[2 * (k1 + 1)]), __uint_as_float(sv[2 * (k1 + 1) + 1]));
-                        else if (k1 == 15) Sn = cmake(S16, 0.0f);
-                        else Sn = cmake(__uint_as_float(sv[30]), -__uint_as_float(sv[31]));   // S[17] = conj S[15]
-                        const cpx Up = cmul(Sn, tw_s[(k1 + 1) * 32 + n2]);
-                        const cpx T = cfma_s(cadd(Um, Up), -wc, Uc);
-                        tre[k1 - 1] = T.re; tim[k1 - 1] = T.im;
-                        Um = Uc; Uc = Up;
-                    }
-                    // A operand of stage 2: rows n2, M-group = frame pair, 16 consecutive floats per frame
-                    {
-                        const uint32_t rowb = (uint32_t)((fl >> 1) * 4096 + n2 * 128);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t unit = (uint32_t)((fl & 1) * 2 + (i >> 1));
-                            const uint32_t o = rowb + (((unit ^ ((uint32_t)n2 & 3u)) << 5) | (uint32_t)((i & 1) << 4));
-                            float4 rh, rl, ih, il;
-                            rh.x = tf32_hi(tre[4 * i]); rh.y = tf32_hi(tre[4 * i + 1]); rh.z = tf32_hi(tre[4 * i + 2]); rh.w = tf32_hi(tre[4 * i + 3]);
-                            rl.x = tre[4 * i] - rh.x; rl.y = tre[4 * i + 1] - rh.y; rl.z = tre[4 * i + 2] - rh.z; rl.w = tre[4 * i + 3] - rh.w;
-                            ih.x = tf32_hi(tim[4 * i]); ih.y = tf32_hi(tim[4 * i + 1]); ih.z = tf32_hi(tim[4 * i + 2]); ih.w = tf32_hi(tim[4 * i + 3]);
-                            il.x = tim[4 * i] - ih.x; il.y = tim[4 * i + 1] - ih.y; il.z = tim[4 * i + 2] - ih.z; il.w = tim[4 * i + 3] - ih.w;
-                            *reinterpret_cast<float4*>(a2_s + 0 * 16384 + o) = rh;
-                            *reinterpret_cast<float4*>(a2_s + 1 * 16384 + o) = rl;
-                            *reinterpret_cast<float4*>(a2_s + 2 * 16384 + o) = ih;
-                            *reinterpret_cast<float4*>(a2_s + 3 * 16384 + o) = il;
-                        }
-                    }
-                    // k1 = 0: 32-point DFT of the real sequence T0[n2] across the warp (radix-2 DIF, bit-reversed result)
-                    {
-                        cpx y = cmake(T0, 0.0f);
-#pragma unroll
-                        for (int s = 0; s < 5; ++s) {
-                            const int half = 16 >> s;
-                            cpx q;
-                            q.re = __shfl_xor_sync(0xffffffffu, y.re, half);
-                            q.im = __shfl_xor_sync(0xffffffffu, y.im, half);
-                            const cpx w = w32_s[(lane & (half - 1)) << s];
-                            y = (lane & half) ? cmul(csub(q, y), w) : cadd(y, q);
-                        }
-                        const int k2 = brev5(lane);
-                        if (k2 <= 16) {
-                            mag0_s[(uu * TCM_UNIT + fl) * 20 + k2] = kb_sqrt(cnorm(y));
-                            if (p.dbg) {
-                                const int t = t0 + uu * TCM_UNIT + fl;
-                                if (t < p.T) p.dbg[((long long)sig * p.T + t) * 513 + 32 * k2] = make_float2(y.re, y.im);
-                            }
-                        }
-                    }
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+                const bool has_next = tile + (int)gridDim.x < n_tiles;
+                const uint32_t pk = (uint32_t)(k & 1), pk1 = (uint32_t)((k - 1) & 1);
+                bar_wait(a2_ready, 0u);                           // unit 0: the (2k)-th completion
+                if (k > 0) bar_wait(d2_free + 0, pk1);
+                issue_s2(0);
+                if (has_next) {
+                    bar_wait(smp_ready, pk ^ 1u);                 // tile k+1 staged (its (k+1)-th completion)
+                    bar_wait(d1_free + 0, pk);                    // X has read D1 slot 0 of tile k
+                    issue_s1(0);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                role_sync(1);
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue_s2(uu);
+                bar_wait(a2_ready, 1u);                           // unit 1: the (2k+1)-th completion
+                if (k > 0) bar_wait(d2_free + 1, pk1);
+                issue_s2(1);
+                if (has_next) {
+                    bar_wait(d1_free + 1, pk);
+                    issue_s1(1);
                 }
             }
+        }
+    } else if (warp < 8) {
+        // =========================================== role X ===========================================================
+        // ---- sample staging: global -> raw_s (cp.async, one tile ahead) -> (hi, lo) swizzled rows ---------------------
+        // Element i of a tile is sample s0 + i of the signal (zero outside [0, L): pad_begin / pad_end / tails).  The copies
+        // are issued a whole unit before their values are split, so their latency hides behind the between-stages step;
+        // V = 4 / 2 / 1 floats per copy by the alignment of the tile's first sample.  A thread splits exactly the
+        // elements it copied, so no barrier is needed in between.
+        int pmode = 1;
+        const int n_el = tile_rows * 32;
+        auto tile_src = [&](int tile, const float*& xsig, long long& s0, int& t0, int& sig) {
+            sig = tile / p.n_tiles_t;
+            const int tt = tile - sig * p.n_tiles_t;
+            const int b = sig / p.C, c = sig - b * p.C;
+            t0 = tt * TCM_TF;
+            xsig = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc;
+            s0 = (long long)t0 * p.hop - p.pad_left;
+        };
+        auto cp_elem = [&](int i, const float* xsig, long long s) {
+            if (s >= 0 && s < p.L)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(raw_s + i)), "l"(xsig + s) : "memory");
+            else raw_s[i] = 0.0f;
+        };
+        // Every thread owns the same 4-element groups i = 4 (tid + 256 it) in every alignment mode, so a thread that is
+        // already copying the next tile never touches raw_s elements another thread has not split yet.
+        auto prefetch = [&](const float* xsig, long long s0) {
+            const unsigned al = (unsigned)((reinterpret_cast<uintptr_t>(xsig) + (uintptr_t)(s0 * 4)) >> 2) & 3u;
+            pmode = (al == 0) ? 4 : ((al & 1u) == 0 ? 2 : 1);
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int i = 4 * (tid + TCM_XT * it);
+                const long long s = s0 + i;
+                if (i < n_el) {
+                    const bool inside = s >= 0 && s + 3 < p.L;
+                    if (inside && pmode == 4) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(raw_s + i)), "l"(xsig + s) : "memory");
+                    } else if (inside && pmode == 2) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(raw_s + i)), "l"(xsig + s) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(raw_s + i + 2)), "l"(xsig + s + 2) : "memory");
+                    } else {
+                        cp_elem(i, xsig, s); cp_elem(i + 1, xsig, s + 1); cp_elem(i + 2, xsig, s + 2); cp_elem(i + 3, xsig, s + 3);
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto commit_stage = [&]() {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int i = 4 * (tid + TCM_XT * it);
+                if (i < n_el) {
+                    const float4 v = *reinterpret_cast<const float4*>(raw_s + i);
+                    const uint32_t o = swz((uint32_t)i >> 5, (uint32_t)i & 31u);
+                    float4 h, l;
+                    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    *reinterpret_cast<float4*>(hi_s + o) = h;
+                    *reinterpret_cast<float4*>(lo_s + o) = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(smp_ready);
+        };
+
+        // ---- between the stages, part 1 (registers only): one thread per row (frame = warp, n2 = lane) --------------------
+        float tre[16], tim[16], mag0v = 0.0f;
+        cpx y0v = cmake(0.0f, 0.0f);
+        auto between_compute = [&](int uu) {
+            const int n2 = lane;
+            uint32_t sv[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(uu * 64 + (warp >> 2) * 32), sv);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(d1_free + uu);                          // D1 slot uu may be overwritten by the next tile's stage 1
+            if (p.ablate & 2) { for (int i = 0; i < 16; ++i) { tre[i] = __uint_as_float(sv[i]); tim[i] = __uint_as_float(sv[16 + i]); } return; }
+            const float S0 = __uint_as_float(sv[0]), S16 = __uint_as_float(sv[1]);
+            const float wc = p.wc;
+            const cpx U0 = cmake(tw_s[n2].re * S0, 0.0f);
+            cpx Uc = cmul(cmake(__uint_as_float(sv[2]), __uint_as_float(sv[3])), tw_s[1 * 32 + n2]);
+            const float T0 = U0.re - 2.0f * wc * Uc.re;       // k1 = 0: real (U[-1] = conj U[1])
+            cpx Um = U0;
+#pragma unroll
+            for (int k1 = 1; k1 <= 16; ++k1) {
+                cpx Sn;
+                if (k1 < 15) Sn = cmake(__uint_as_float(sv[2 * (k1 + 1)]), __uint_as_float(sv[2 * (k1 + 1) + 1]));
+                else if (k1 == 15) Sn = cmake(S16, 0.0f);
+                else Sn = cmake(__uint_as_float(sv[30]), -__uint_as_float(sv[31]));   // S[17] = conj S[15]
+                const cpx Up = cmul(Sn, tw_s[(k1 + 1) * 32 + n2]);
+                const cpx T = cfma_s(cadd(Um, Up), -wc, Uc);
+                tre[k1 - 1] = T.re; tim[k1 - 1] = T.im;
+                Um = Uc; Uc = Up;
+            }
+            // k1 = 0: 32-point DFT of the real sequence T0[n2] across the warp (radix-2 DIF, bit-reversed result)
+            cpx y = cmake(T0, 0.0f);
+#pragma unroll
+            for (int s5 = 0; s5 < 5; ++s5) {
+                const int half = 16 >> s5;
+                cpx q;
+                q.re = __shfl_xor_sync(0xffffffffu, y.re, half);
+                q.im = __shfl_xor_sync(0xffffffffu, y.im, half);
+                const cpx w = w32_s[(lane & (half - 1)) << s5];
+                y = (lane & half) ? cmul(csub(q, y), w) : cadd(y, q);
+            }
+            y0v = y;
+            mag0v = kb_sqrt(cnorm(y));
+        };
+        // part 2 (after the A operand buffer and the mag0 slot are free): split, store, signal the issuer
+        auto between_store = [&](int uu, int t0, int sig) {
+            const int n2 = lane, fl = warp;
+            const uint32_t rowb = (uint32_t)((fl >> 1) * 4096 + n2 * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t unit = (uint32_t)((fl & 1) * 2 + (i >> 1));
+                const uint32_t o = rowb + (((unit ^ ((uint32_t)n2 & 3u)) << 5) | (uint32_t)((i & 1) << 4));
+                float4 rh, rl, ih, il;
+                rh.x = tf32_rn(tre[4 * i]); rh.y = tf32_rn(tre[4 * i + 1]); rh.z = tf32_rn(tre[4 * i + 2]); rh.w = tf32_rn(tre[4 * i + 3]);
+                rl.x = tre[4 * i] - rh.x; rl.y = tre[4 * i + 1] - rh.y; rl.z = tre[4 * i + 2] - rh.z; rl.w = tre[4 * i + 3] - rh.w;
+                ih.x = tf32_rn(tim[4 * i]); ih.y = tf32_rn(tim[4 * i + 1]); ih.z = tf32_rn(tim[4 * i + 2]); ih.w = tf32_rn(tim[4 * i + 3]);
+                il.x = tim[4 * i] - ih.x; il.y = tim[4 * i + 1] - ih.y; il.z = tim[4 * i + 2] - ih.z; il.w = tim[4 * i + 3] - ih.w;
+                *reinterpret_cast<float4*>(a2_s + 0 * 16384 + o) = rh;
+                *reinterpret_cast<float4*>(a2_s + 1 * 16384 + o) = rl;
+                *reinterpret_cast<float4*>(a2_s + 2 * 16384 + o) = ih;
+                *reinterpret_cast<float4*>(a2_s + 3 * 16384 + o) = il;
+            }
+            const int k2 = brev5(lane);
+            if (k2 <= 16) {
+                mag0_s[(uu * TCM_UNIT + fl) * 20 + k2] = mag0v;
+                if (p.dbg) {
+                    const int t = t0 + uu * TCM_UNIT + fl;
+                    if (t < p.T) p.dbg[((long long)sig * p.T + t) * 513 + 32 * k2] = make_float2(y0v.re, y0v.im);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A operand: generic stores -> async proxy
+            bar_arrive(a2_ready);
+        };
+
+        // ---- tile loop (per thread, no barrier among the X warps) -----------------------------------------------------------
+        int k = 0;                                              // this CTA's tile counter
+        const float* xsig; long long s0; int t0, sig;
+        if ((int)blockIdx.x < n_tiles) {
+            tile_src((int)blockIdx.x, xsig, s0, t0, sig);
+            prefetch(xsig, s0);
+            commit_stage();
+        }
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const bool has_next = tile + (int)gridDim.x < n_tiles;
+            const int t0c = t0, sigc = sig;                      // this tile (for the debug dump)
+            const uint32_t pk = (uint32_t)(k & 1), pk1 = (uint32_t)((k - 1) & 1);
+            if (has_next) {
+                tile_src(tile + (int)gridDim.x, xsig, s0, t0, sig);
+                prefetch(xsig, s0);                             // raw_s was consumed by this thread's previous commit_stage
+            }
+            // ---- unit 0 ----
+            bar_wait(s1_done + 0, pk);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            between_compute(0);
+            if (k > 0) {
+                bar_wait(s2_done + 1, pk1);                     // stage 2 of the previous unit has read the A buffer
+                bar_wait(d2_free + 0, pk1);                     // Y has read mag0 slot 0 of the previous tile
+            }
+            between_store(0, t0c, sigc);
+            // ---- unit 1 ----
+            bar_wait(s1_done + 1, pk);                          // both stage-1 GEMMs of the tile are done: hi_s / lo_s are free
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            between_compute(1);
+            if (has_next) commit_stage();
+            bar_wait(s2_done + 0, pk);
+            if (k > 0) bar_wait(d2_free + 1, pk1);
+            between_store(1, t0c, sigc);
         }
     } else {
         // =========================================== role Y ===========================================================
@@ -343,6 +451,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
             for (int uu = 0; uu < 2; ++uu) {
                 bar_wait(s2_done + uu, (uint32_t)(k & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (p.ablate & 1) { bar_arrive(d2_free + uu); continue; }
                 // ---- stage-2 accumulators -> magnitudes (row = (frame, k1), 16 of the 32 k2 per thread) ---------------
                 {
                     const int fl = 2 * q + (lane >> 4), k1 = 1 + (lane & 15);
@@ -350,6 +459,12 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
                     const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + uu * 64 + 16 * h);
                     tmem_ld16(ta, re);
                     tmem_ld16(ta + 32, im);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    float m0 = 0.0f;
+                    int f0 = 0, k2c = 0;
+                    const bool copier = ty < TCM_UNIT * 17;     // bins 0, 32, .., 512 come from the X role's shuffle DFT
+                    if (copier) { f0 = ty / 17; k2c = ty - f0 * 17; m0 = mag0_s[(uu * TCM_UNIT + f0) * 20 + k2c]; }
+                    bar_arrive(d2_free + uu);                   // D2 slot uu and mag0 slot uu may be overwritten
                     float* mrow = mag_s + fl * TCM_MS;
                     const int t = t0 + uu * TCM_UNIT + fl;
                     if (!(h == 1 && k1 == 16)) {          // k1 = 16, k2 >= 16 mirrors onto the k1 = 16, k2 < 16 bins
@@ -362,17 +477,11 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
                             if (p.dbg && t < p.T) p.dbg[((long long)sig * p.T + t) * 513 + bin] = make_float2(xr, h ? -xi : xi);
                         }
                     }
-                    // bins 0, 32, .., 512 from the X role's shuffle DFT
-                    if (ty < TCM_UNIT * 17) {
-                        const int f0 = ty / 17, k2 = ty - f0 * 17;
-                        mag_s[f0 * TCM_MS + 32 * k2] = mag0_s[(uu * TCM_UNIT + f0) * 20 + k2];
-                    }
+                    if (copier) mag_s[f0 * TCM_MS + 32 * k2c] = m0;
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 role_sync(2);
-                if (ty == 0) bar_arrive(d2_free + uu);      // D2 slot and mag0 slot may be overwritten
                 // ---- mel filterbank: 32 lane groups x 8 frames walk the 4-bin chunk lists ----------------------------
-                {
+                if (!(p.ablate & 8)) {
                     const int grp = ty >> 3, f = ty & 7;
                     const float* mrow = mag_s + f * TCM_MS;
                     float a0 = 0.0f, a1 = 0.0f;
@@ -405,7 +514,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
                         }
                     }
                 }
-                // next unit's magnitudes may be written now: every Y thread passed the barrier after the filterbank;
+                // the next unit's magnitudes may be written now (every Y thread passed the barrier after the filterbank);
                 // out_s is rewritten only after the next role_sync
             }
             if (p.db) {

@@ -42,3 +42,42 @@ def test_tc_dft_stage1_vs_oracle(items, length):
     for i in range(items):
         scale = np.abs(exp[i]).max()
         assert np.abs(got[i] - exp[i]).max() < 2e-6 * scale, (i, np.abs(got[i] - exp[i]).max() / scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('hop,pads', [(256, (False, False)), (128, (True, True)), (256, (True, False))])
+def test_tc_fused_logmel_kernel_vs_oracle(monkeypatch, hop, pads):
+    """The complete tensor-core pipeline (kapre_b200/csrc/tc_mel.cuh, opt-in with KAPRE_B200_TC=1): both FFT stages as
+    tcgen05 GEMMs, the Hann window as a 3-tap filter between them.  Its complex spectrum (debug dump), mel and dB outputs
+    against the float64 oracle: 2e-6 of the item's largest value (3xTF32 split with round-to-nearest hi parts)."""
+    import ctypes
+    import kapre_b200 as K
+    from kapre_b200 import _native
+    monkeypatch.setenv('KAPRE_B200_TC', '1')
+    rng = np.random.default_rng(hop)
+    B, L = 3, 1024 + 256 * 41 + 13
+    x = rng.uniform(-1, 1, size=(B, 1, L)).astype(np.float32)
+    x[2] *= 1e-3
+    kw = dict(n_fft=1024, hop_length=hop, sample_rate=22050, n_mels=128, pad_begin=pads[0], pad_end=pads[1],
+              input_data_format='channels_first', output_data_format='channels_first')
+    ref_spec = O.stft_layer(x, 1024, None, hop, None, pads[0], pads[1], 'channels_first', 'channels_first')[:, 0]
+    T = ref_spec.shape[1]
+    dbg = torch.zeros((B, T, 513), dtype=torch.complex64, device='cuda')
+    _native.lib().kapre_tc_set_debug(ctypes.c_void_p(dbg.data_ptr()))
+    mel = K.get_melspectrogram_layer(**kw)(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert _native.last_launch_info().startswith('TC tcgen05')
+    spec = dbg.cpu().numpy()
+    refm = O.melspectrogram_layer(x, **kw)
+    for b in range(B):
+        assert np.abs(spec[b] - ref_spec[b]).max() < 2e-6 * np.abs(ref_spec[b]).max()
+        assert np.abs(mel[b] - refm[b]).max() < 2e-6 * np.abs(refm[b]).max()
+    db = K.get_melspectrogram_layer(return_decibel=True, **kw)(torch.from_numpy(x).cuda()).cpu().numpy()
+    refdb = O.melspectrogram_layer(x, return_decibel=True, **kw)
+    assert np.abs(db - refdb).max() < 2e-4
+    # a hamming window takes the same path (a - b cos with a = 0.54, b = 0.46)
+    kwh = dict(kw, window_name='hamming_window')
+    melh = K.get_melspectrogram_layer(**kwh)(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert _native.last_launch_info().startswith('TC tcgen05')
+    refh = O.melspectrogram_layer(x, **kwh)
+    for b in range(B):
+        assert np.abs(melh[b] - refh[b]).max() < 2e-6 * np.abs(refh[b]).max()
