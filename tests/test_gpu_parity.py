@@ -377,6 +377,41 @@ def test_cfg2_full_size_properties(K):
     assert float((ydb.double() - expect).abs().max()) < 1e-4
 
 
+def test_full_tensor_blocks_of_16_items_cfg2_and_cfg3(K):
+    """Full-tensor (every element, not spot checks) oracle comparison of 16-item blocks at the BASELINE sizes:
+    cfg2 log-mel (16 x 5 s, n_fft 1024, hop 256, 128 mel, dB) and cfg3 (16 x 6 channels x 1 s channels_last, n_fft 2048,
+    hop 1024, magnitude + dB).  Linear outputs at 2e-6 of the block maximum; dB values wherever the linear value is above
+    1e-6 of the item peak (below that the fp32 FFT noise floor under a logarithm is not a parity statement) at 1e-3 dB."""
+    g = torch.Generator(device='cuda').manual_seed(77)
+    x2 = (torch.rand((16, 110250, 1), generator=g, device='cuda') * 2 - 1)
+    x2[3] *= 1e-3
+    kw2 = dict(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128)
+    lin = K.get_melspectrogram_layer(**kw2)(x2).cpu().numpy()
+    db = K.get_melspectrogram_layer(return_decibel=True, **kw2)(x2).cpu().numpy()
+    xn = x2.cpu().numpy()
+    ref_lin = O.melspectrogram_layer(xn, **kw2)
+    ref_db = O.melspectrogram_layer(xn, return_decibel=True, **kw2)
+    assert lin.shape == ref_lin.shape == (16, 427, 128, 1)
+    for i in range(16):
+        assert np.abs(lin[i] - ref_lin[i]).max() < 2e-6 * np.abs(ref_lin[i]).max(), i
+        sig = ref_lin[i] > 1e-6 * ref_lin[i].max()
+        assert sig.mean() > 0.99
+        assert np.abs(db[i] - ref_db[i])[sig].max() < 1e-3, i
+    x3 = (torch.rand((16, 44100, 6), generator=g, device='cuda') * 2 - 1)
+    x3[:, :, 4] *= 1e-2
+    kw3 = dict(n_fft=2048, hop_length=1024, input_data_format='channels_last', output_data_format='channels_last')
+    mag = K.get_stft_magnitude_layer(**kw3)(x3).cpu().numpy()
+    mdb = K.get_stft_magnitude_layer(return_decibel=True, **kw3)(x3).cpu().numpy()
+    xn3 = x3.cpu().numpy()
+    ref_mag = O.stft_magnitude_layer(xn3, **kw3)
+    ref_mdb = O.stft_magnitude_layer(xn3, return_decibel=True, **kw3)
+    assert mag.shape == ref_mag.shape == (16, 42, 1025, 6)
+    for i in range(16):
+        assert np.abs(mag[i] - ref_mag[i]).max() < 2e-6 * np.abs(ref_mag[i]).max(), i
+        sig = ref_mag[i] > 1e-5 * ref_mag[i].max()
+        assert np.abs(mdb[i] - ref_mdb[i])[sig].max() < 2e-3, i
+
+
 # ------------------------------------------------------------------------------- C ABI behaviour
 def test_abi_errors_and_config(K):
     from kapre_b200 import _native, ops
