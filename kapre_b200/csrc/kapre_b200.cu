@@ -327,6 +327,7 @@ struct kapre_stft_plan {
     double win_a = 0.0, win_b = 0.0;
     float* tc_f1 = nullptr;   // stage-1 matrix hi/lo
     float* tc_cs = nullptr;   // stage-2 C / S matrices hi/lo
+    unsigned short* tc_csb = nullptr;   // the same matrices in bf16 (lo-part products)
     float2* tc_tw = nullptr;  // a e^{-2 pi i n2 k1 / 1024}
     float2* tc_w32 = nullptr; // e^{-2 pi i j / 32}
 };
@@ -358,6 +359,20 @@ static int kb_tc_tables(kapre_stft_plan* p) {
     for (int n2 = 0; n2 < 32; ++n2)
         for (int k2 = 0; k2 < 32; ++k2) M[n2 * 32 + k2] = sin(2.0 * M_PI * (double)((n2 * k2) % 32) / 32.0);
     kb_tc_pack_b(M.data(), cs.data() + 2048, cs.data() + 3072);
+    // bf16 copies of C and S, K-major interleaved (4 kchunk, 32 col, 8)
+    std::vector<unsigned short> csb(2048);
+    for (int which = 0; which < 2; ++which)
+        for (int kc = 0; kc < 4; ++kc)
+            for (int c = 0; c < 32; ++c)
+                for (int e = 0; e < 8; ++e) {
+                    const int n2 = 8 * kc + e;
+                    const double a = 2.0 * M_PI * (double)((n2 * c) % 32) / 32.0;
+                    const float w = (float)(which ? sin(a) : cos(a));
+                    uint32_t u;
+                    memcpy(&u, &w, 4);
+                    u += 0x7fffu + ((u >> 16) & 1u);                 // round to nearest even
+                    csb[(size_t)which * 1024 + (kc * 32 + c) * 8 + e] = (unsigned short)(u >> 16);
+                }
     std::vector<float2> tw(18 * 32), w32(16);
     for (int k1 = 0; k1 < 18; ++k1)
         for (int n2 = 0; n2 < 32; ++n2) {
@@ -369,7 +384,7 @@ static int kb_tc_tables(kapre_stft_plan* p) {
         w32[j] = make_float2((float)cos(a), (float)sin(a));
     }
     int rc;
-    if ((rc = kb_upload(f1, &p->tc_f1)) || (rc = kb_upload(cs, &p->tc_cs)) || (rc = kb_upload(tw, &p->tc_tw)) ||
+    if ((rc = kb_upload(f1, &p->tc_f1)) || (rc = kb_upload(cs, &p->tc_cs)) || (rc = kb_upload(csb, &p->tc_csb)) || (rc = kb_upload(tw, &p->tc_tw)) ||
         (rc = kb_upload(w32, &p->tc_w32)))
         return rc;
     return 0;
@@ -395,6 +410,9 @@ struct kapre_filterbank {
     kb_f4* cw = nullptr;
     kb_i2* cm = nullptr;
     int* cg = nullptr;
+    int n_bd = 0;              // band descriptors of the two-level walk (kb_make_fb_band_desc)
+    kb_i2* bd = nullptr;
+    int* bg = nullptr;
     int n_msteps = 0;          // tensor-core form (kb_make_fb_mma) for the fused kernel
     kb_f4* mw = nullptr;
     kb_i2* ms = nullptr;
@@ -788,7 +806,7 @@ int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const floa
 void kapre_stft_plan_destroy(kapre_stft_plan* p) {
     if (!p) return;
     cudaFree(p->wh); cudaFree(p->cwq); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->w); cudaFree(p->tw);
-    cudaFree(p->tc_f1); cudaFree(p->tc_cs); cudaFree(p->tc_tw); cudaFree(p->tc_w32);
+    cudaFree(p->tc_f1); cudaFree(p->tc_cs); cudaFree(p->tc_csb); cudaFree(p->tc_tw); cudaFree(p->tc_w32);
     delete p;
 }
 
@@ -924,7 +942,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
             q.x = x_dev; q.x_sb = xd->stride_b; q.x_sc = xd->stride_c;
             q.B = B; q.C = C; q.L = Ln; q.T = T; q.hop = plan->hop; q.pad_left = pad_left;
             q.wc = (float)(plan->win_b / (2.0 * plan->win_a));
-            q.f1 = plan->tc_f1; q.cs = plan->tc_cs; q.tw = plan->tc_tw; q.w32 = plan->tc_w32;
+            q.f1 = plan->tc_f1; q.cs = plan->tc_cs; q.csb = plan->tc_csb; q.tw = plan->tc_tw; q.w32 = plan->tc_w32;
             q.cw = fb->cw; q.cm = fb->cm; q.cg = fb->cg; q.n_chunks = fb->n_chunks; q.n_bands = fb->n_bands;
             q.out = (float*)out_dev; q.o_sb = od->stride_b; q.o_sc = od->stride_c; q.o_st = od->stride_t; q.o_sk = od->stride_f;
             q.db = dbmode ? 1 : 0;
@@ -976,6 +994,8 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         p.bands = fb->bands; p.fbw = fb->w; p.n_bands = fb->n_bands; p.n_fbw = fb->n_w;
         p.cw = fb->cw; p.cm = fb->cm; p.cg = fb->cg; p.n_chunks = fb->n_chunks;
         p.mw = fb->mw; p.ms = fb->ms; p.mg = fb->mg; p.n_msteps = fb->n_msteps;
+        p.bd = fb->bd; p.bg = fb->bg; p.n_bd = fb->n_bd;
+        p.fb_bands = (fb->bd && kb_env_int("KAPRE_B200_FBBANDS", 1)) ? 1 : 0;
     }
     if (dbmode) {
         p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev;
@@ -1184,6 +1204,10 @@ int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre
         if ((rc = kb_upload(cw, &f->cw)) || (rc = kb_upload(cm, &f->cm)) || (rc = kb_upload(cg, &f->cg))) {
             kapre_filterbank_destroy(f); return rc;
         }
+        std::vector<kb_i2> bd; std::vector<int> bg;
+        kb_make_fb_band_desc(cm, cg, 32, bd, bg);
+        f->n_bd = (int)bd.size();
+        if ((rc = kb_upload(bd, &f->bd)) || (rc = kb_upload(bg, &f->bg))) { kapre_filterbank_destroy(f); return rc; }
         std::vector<kb_f4> mw; std::vector<kb_i2> ms; std::vector<int> mg;
         kb_make_fb_mma(fb_host, n_freq, n_bands, mw, ms, mg);
         f->n_msteps = (int)ms.size();
@@ -1198,7 +1222,7 @@ int kapre_filterbank_create(const float* fb_host, int n_freq, int n_bands, kapre
 void kapre_filterbank_destroy(kapre_filterbank* f) {
     if (!f) return;
     cudaFree(f->bands); cudaFree(f->w); cudaFree(f->cw); cudaFree(f->cm); cudaFree(f->cg);
-    cudaFree(f->mw); cudaFree(f->ms); cudaFree(f->mg);
+    cudaFree(f->mw); cudaFree(f->ms); cudaFree(f->mg); cudaFree(f->bd); cudaFree(f->bg);
     delete f;
 }
 

@@ -82,6 +82,11 @@ struct KbStftParams {
     const kb_i2* cm;
     const int* cg;
     int n_chunks;
+    // two-level form (kb_make_fb_band_desc): fb_bands = 1 makes the single-channel kernel walk band descriptors
+    int fb_bands;
+    const kb_i2* bd;
+    const int* bg;
+    int n_bd;
     // tensor-core form (kb_make_fb_mma): fb_mma = 1 runs the filterbank phase as a block-banded
     // mma.sync m16n8k8 3xTF32 GEMM; mw is read from global memory (L2-resident), ms / mg are staged.
     int fb_mma;

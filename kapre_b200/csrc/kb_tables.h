@@ -157,6 +157,28 @@ static inline void kb_make_fb_chunks(const float* fb, int n_freq, int n_bands, i
     cg[groups] = (int)cw.size();
 }
 
+// Band descriptors for the two-level form of the same chunk lists (the chunks of a band are consecutive in cw): group g
+// owns descriptors [bg[g], bg[g+1]); descriptor = (first bin | chunks << 16, band | first chunk << 16).  The fused kernel's
+// filterbank phase then runs an inner loop without the per-chunk "last chunk of the band?" test.
+static inline void kb_make_fb_band_desc(const std::vector<kb_i2>& cm, const std::vector<int>& cg, int groups,
+                                        std::vector<kb_i2>& bd, std::vector<int>& bg) {
+    bd.clear(); bg.assign(groups + 1, 0);
+    for (int g = 0; g < groups; ++g) {
+        bg[g] = (int)bd.size();
+        int first = cg[g];
+        for (int i = cg[g]; i < cg[g + 1]; ++i) {
+            if (cm[i].y >= 0) {                       // last chunk of a band
+                kb_i2 d;
+                d.x = cm[first].x | ((i - first + 1) << 16);
+                d.y = cm[i].y | (first << 16);
+                bd.push_back(d);
+                first = i + 1;
+            }
+        }
+    }
+    bg[groups] = (int)bd.size();
+}
+
 // Tensor-core form of the filterbank for the fused kernel (mma.sync m16n8k8, 3xTF32 split): the
 // (frames x bins) . (bins x bands) product is tiled into 8-band column tiles; tile j only needs the
 // k-steps (8 bins each) its bands' supports touch (block-banded GEMM: ~17 % of the dense tile grid for a

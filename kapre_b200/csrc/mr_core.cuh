@@ -27,9 +27,11 @@ struct KbMrParams {
     int TF;                   // frames per tile (= frames per warp per tile * n_warps)
 };
 
-// radices of P in {4, 2, 3, 5} order (4s first: fewest passes); returns -1 if P has another prime factor
+// radices of P in {8, 4, 2, 3, 5} order (large radices first: fewest passes over shared memory); returns -1 if P has
+// another prime factor
 static inline int kb_mr_factor(int P, int* radix) {
     int n = 0;
+    while (P % 8 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 8; P /= 8; }
     while (P % 4 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 4; P /= 4; }
     while (P % 2 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 2; P /= 2; }
     while (P % 3 == 0 && n < KB_MR_MAX_PASS) { radix[n++] = 3; P /= 3; }
@@ -53,6 +55,20 @@ KB_HD void kb_dft_r2(cpx* v) { const cpx a = v[0], b = v[1]; v[0] = cadd(a, b); 
 KB_HD void kb_dft_r4(cpx* v) {
     const cpx a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = kb_mul_mi(csub(v[1], v[3]));
     v[0] = cadd(a, c); v[2] = csub(a, c); v[1] = cadd(b, d); v[3] = csub(b, d);
+}
+KB_HD void kb_dft_r8(cpx* v) {
+    // two radix-4 butterflies on the even / odd inputs, then the radix-2 combination with W_8^k
+    cpx e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    kb_dft_r4(e);
+    kb_dft_r4(o);
+    const float h = 0.70710678118654752440f;
+    const cpx o1 = cscale(cadd(o[1], kb_mul_mi(o[1])), h);            // o1 * (1 - i) / sqrt2
+    const cpx o2 = kb_mul_mi(o[2]);                                    // o2 * (-i)
+    const cpx o3 = cscale(csub(kb_mul_mi(o[3]), o[3]), h);            // o3 * (-1 - i) / sqrt2
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+    v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
 }
 KB_HD void kb_dft_r3(cpx* v) {
     const cpx t1 = cadd(v[1], v[2]);
@@ -83,12 +99,15 @@ KB_FN void kb_mr_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const c
 #pragma unroll
         for (int t = 0; t < RDX; ++t) v[t] = in[j + t * nb];
         if (Ns > 1) {
+            const int kt = k * tstep;
+            int ti = kt;
 #pragma unroll
-            for (int t = 1; t < RDX; ++t) v[t] = cmul(v[t], tw_s[t * k * tstep]);
+            for (int t = 1; t < RDX; ++t) { v[t] = cmul(v[t], tw_s[ti]); ti += kt; }
         }
         if (RDX == 2) kb_dft_r2(v);
         else if (RDX == 3) kb_dft_r3(v);
         else if (RDX == 4) kb_dft_r4(v);
+        else if (RDX == 8) kb_dft_r8(v);
         else kb_dft_r5(v);
         const int j0 = (j - k) * RDX + k;
 #pragma unroll
@@ -139,7 +158,21 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
                 cpx* A = reinterpret_cast<cpx*>(smem + L.buf + (warp * 2) * bufsz);
                 if (t < p.T) {
                     const long long s0 = (long long)t * p.hop - p.pad_left;
-                    if (q.half) {
+                    const bool interior = s0 >= 0 && s0 + N <= p.L && We == N && p.x_sl == 1 &&
+                                          (((reinterpret_cast<uintptr_t>(xsig) >> 2) + (uintptr_t)s0) & 1u) == 0;
+                    if (q.half && interior) {
+                        // whole frame inside the signal, 8-byte aligned: one vector load of (x[2n], x[2n+1]) and of the window pair
+                        const float2* xp = reinterpret_cast<const float2*>(xsig + s0);
+                        const float2* wp = reinterpret_cast<const float2*>(p.w);
+                        for (int n = lane; n < P; n += 32) {
+#if defined(KB_HOST_EMU)
+                            const float2 xv = xp[n], wv = wp[n];
+#else
+                            const float2 xv = __ldg(xp + n), wv = __ldg(wp + n);
+#endif
+                            A[n] = cmake(xv.x * wv.x, xv.y * wv.y);
+                        }
+                    } else if (q.half) {
                         for (int n = lane; n < P; n += 32) {
                             float v[2];
 #pragma unroll
@@ -172,7 +205,8 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
                     const cpx* in = (ps & 1) ? b1 : b0;
                     cpx* out = (ps & 1) ? b0 : b1;
                     if (t < p.T) {
-                        if (r == 4) kb_mr_pass<4>(in, out, tw_s, P, Ns, lane);
+                        if (r == 8) kb_mr_pass<8>(in, out, tw_s, P, Ns, lane);
+                        else if (r == 4) kb_mr_pass<4>(in, out, tw_s, P, Ns, lane);
                         else if (r == 2) kb_mr_pass<2>(in, out, tw_s, P, Ns, lane);
                         else if (r == 3) kb_mr_pass<3>(in, out, tw_s, P, Ns, lane);
                         else kb_mr_pass<5>(in, out, tw_s, P, Ns, lane);

@@ -594,6 +594,10 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
             for (int i = tid; i < p.n_msteps; i += kb_nt) cm_s[i] = p.ms[i];
             for (int i = tid; i <= KB_MMA_SLOTS; i += kb_nt) cg_s[i] = p.mg[i];
             for (int i = tid; i < TF * L.Mp; i += kb_nt) out_s[i] = 0.0f;   // the phase accumulates into a zeroed tile
+        } else if (fbmode && p.fb_bands) {   // band descriptors live where the per-chunk descriptors would (n_bd <= n_chunks)
+            for (int i = tid; i < p.n_chunks; i += kb_nt) cw_s[i] = p.cw[i];
+            for (int i = tid; i < p.n_bd; i += kb_nt) cm_s[i] = p.bd[i];
+            for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.bg[i];
         } else if (fbmode) {
             for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
             for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.cg[i];
@@ -820,6 +824,44 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
             if (fbmma) {
                 kb_fb_mma_phase<Q>(reinterpret_cast<const float*>(ex_s), 2 * EXS, FR, p.mw, cm_s, cg_s, out_s, L.Mp,
                                    p.n_bands, NW);
+            } else if (p.fb_bands) {
+            // two-level walk: bands of the lane group, then the band's 4-bin chunks (same sums in the same order as the
+            // flat chunk list below, without the per-chunk flush test)
+            KB_PHASE_BEGIN
+                (void)R;
+                const int warp = tid >> 5, lane = tid & 31;
+                const int w = lane % NW;
+                const int grp = warp * (32 / NW) + lane / NW;           // 0..31
+                const float* __restrict__ mw = reinterpret_cast<const float*>(ex_s + w * EXS);
+                float* __restrict__ ocol = out_s + (w * FPW) * L.Mp;
+                const int be = cg_s[grp + 1];
+                for (int bi = cg_s[grp]; bi < be; ++bi) {
+                    const kb_i2 d = cm_s[bi];
+                    const float* mp = mw + (d.x & 0xffff) * FPW;
+                    const kb_f4* __restrict__ wp = cw_s + (d.y >> 16);
+                    const int nch = d.x >> 16;
+                    float a0[FPW], a1[FPW];
+#pragma unroll
+                    for (int g = 0; g < FPW; ++g) { a0[g] = 0.0f; a1[g] = 0.0f; }
+                    for (int c = 0; c < nch; ++c) {
+                        const kb_f4 wv = wp[c];
+                        float m01[2 * FPW], m23[2 * FPW];
+                        kb_load_vec<2 * FPW>(m01, mp);
+                        kb_load_vec<2 * FPW>(m23, mp + 2 * FPW);
+#pragma unroll
+                        for (int g = 0; g < FPW; ++g) {
+                            a0[g] += wv.x * m01[g];
+                            a1[g] += wv.y * m01[FPW + g];
+                            a0[g] += wv.z * m23[g];
+                            a1[g] += wv.w * m23[FPW + g];
+                        }
+                        mp += 4 * FPW;
+                    }
+                    const int m = d.y & 0xffff;
+#pragma unroll
+                    for (int g = 0; g < FPW; ++g) ocol[g * L.Mp + m] = a0[g] + a1[g];
+                }
+            KB_PHASE_END
             } else {
             KB_PHASE_BEGIN
                 (void)R;

@@ -48,6 +48,7 @@ struct KbTcMelParams {
     float wc;                        // b / (2 a) of the window a - b cos(2 pi n / 1024)
     const float* f1;                 // stage-1 matrix, (hi|lo, 8 kchunk, 32 col, 4)
     const float* cs;                 // stage-2 matrices C_hi, C_lo, S_hi, S_lo, each (8 kchunk, 32 col, 4)
+    const unsigned short* csb;       // C, S as bf16 (4 kchunk, 32 col, 8) for the lo-part products (kind::f16)
     const float2* tw;                // [18][32]: a e^{-2 pi i n2 k1 / 1024}, k1 = 0..17
     const float2* w32;               // [16]: e^{-2 pi i j / 32}
     const kb_f4* cw;                 // filterbank chunk lists (kb_make_fb_chunks, 32 groups)
@@ -64,16 +65,18 @@ struct KbTcMelParams {
     int ablate;                      // timing experiments only: 1 Y skips its work, 2 X skips the between-stages math, 4 no MMAs, 8 no filterbank
 };
 
-struct KbTcMelSmem { int hi, lo, a2, raw, f1, cs, tw, w32, mag, outs, mag0, cw, cm, cg, bar, total; };
+struct KbTcMelSmem { int hi, lo, a2, raw, f1, cs, csb, tw, w32, mag, outs, mag0, cw, cm, cg, bar, total; };
+#define TCM_A2_BYTES 49152           // one stage-2 A operand set: re_hi, im_hi (TF32, 16 KB each), re_lo, im_lo (bf16, 8 KB each)
 KB_HD KbTcMelSmem kb_tcm_smem_layout(int n_chunks) {
     KbTcMelSmem s;
     int off = 0;
     s.hi = off; off += TCM_MAXROWS * 128;                  // 19456 = 19 * 1024
     s.lo = off; off += TCM_MAXROWS * 128;
-    s.a2 = off; off += 4 * 16384;                          // A_re hi/lo, A_im hi/lo: 4 groups x 32 rows x 128 B each
+    s.a2 = off; off += 2 * TCM_A2_BYTES;                   // two A operand sets (double buffer: unit 0 / unit 1 of a tile)
     s.raw = off; off += TCM_MAXROWS * 128;                 // next tile's samples as they arrive (cp.async), linear
     s.f1 = off; off += 8192;
     s.cs = off; off += 16384;
+    s.csb = off; off += 4096;
     s.tw = off; off += 18 * 32 * 8;
     s.w32 = off; off += 16 * 8;
     s.mag = off; off += TCM_UNIT * TCM_MS * 4;
@@ -113,6 +116,17 @@ __device__ __forceinline__ float tf32_rn(float v) {
     return __uint_as_float(r);
 }
 __device__ __forceinline__ int brev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
+// two floats -> packed bf16 pair (lo at the lower address)
+__device__ __forceinline__ uint32_t bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// D (+)= A . B with bf16 operands (K = 16), fp32 accumulate; always accumulating
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 
 }  // namespace kbtc
 
@@ -128,6 +142,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
     float* raw_s = reinterpret_cast<float*>(sm + L.raw);
     float* f1_s = reinterpret_cast<float*>(sm + L.f1);
     float* cs_s = reinterpret_cast<float*>(sm + L.cs);
+    unsigned short* csb_s = reinterpret_cast<unsigned short*>(sm + L.csb);
     cpx* tw_s = reinterpret_cast<cpx*>(sm + L.tw);
     cpx* w32_s = reinterpret_cast<cpx*>(sm + L.w32);
     float* mag_s = reinterpret_cast<float*>(sm + L.mag);
@@ -140,18 +155,19 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bar + 96);
     // MMA completion (tcgen05.commit, count 1):          s1_done[2] (stage 1 of unit 0 / 1), s2_done[2]
     // operand written / accumulator read (count 256):    d1_free[2] (X read D1), d2_free[2] (Y read D2 + mag0),
-    //                                                    a2_ready (X wrote the stage-2 A operand), smp_ready (X staged a tile)
+    //                                                    a2_ready[2] (X wrote stage-2 A operand set 0 / 1), smp_ready (X staged a tile)
     uint64_t* s1_done = bars;
     uint64_t* s2_done = bars + 2;
     uint64_t* d1_free = bars + 4;
     uint64_t* d2_free = bars + 6;
-    uint64_t* a2_ready = bars + 8;
-    uint64_t* smp_ready = bars + 9;
+    uint64_t* a2_ready = bars + 8;                          // [2]: one per A operand set
+    uint64_t* smp_ready = bars + 10;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time: constant tables, barriers, TMEM (256 columns) -------------------------------------------------
     for (int i = tid; i < 2048; i += TCM_THREADS) f1_s[i] = p.f1[i];
     for (int i = tid; i < 4096; i += TCM_THREADS) cs_s[i] = p.cs[i];
+    for (int i = tid; i < 2048; i += TCM_THREADS) csb_s[i] = p.csb[i];
     for (int i = tid; i < 18 * 32; i += TCM_THREADS) { const float2 t = p.tw[i]; tw_s[i] = cmake(t.x, t.y); }
     for (int i = tid; i < 16; i += TCM_THREADS) { const float2 t = p.w32[i]; w32_s[i] = cmake(t.x, t.y); }
     for (int i = tid; i < p.n_chunks; i += TCM_THREADS) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
@@ -159,7 +175,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
     for (int i = tid; i < TCM_UNIT * TCM_MS; i += TCM_THREADS) mag_s[i] = 0.0f;     // incl. the pad bins, never written again
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) bar_init(bars + i, 1);
-        for (int i = 4; i < 10; ++i) bar_init(bars + i, TCM_XT);
+        for (int i = 4; i < 11; ++i) bar_init(bars + i, TCM_XT);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
@@ -191,10 +207,17 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
             // moves, by compile-time constants.
             const uint64_t d_ah = make_desc(a_hi, lbo1, 512, 1), d_al = make_desc(a_lo, lbo1, 512, 1);
             const uint64_t d_fh = make_desc(f_hi, 512, 128, 0), d_fl = make_desc(f_lo, 512, 128, 0);
-            const uint64_t d_rh = make_desc(a2 + 0 * 16384, 4096, 512, 1), d_rl = make_desc(a2 + 1 * 16384, 4096, 512, 1);
-            const uint64_t d_ih = make_desc(a2 + 2 * 16384, 4096, 512, 1), d_il = make_desc(a2 + 3 * 16384, 4096, 512, 1);
+            // stage-2 A operand set b at a2 + b * TCM_A2_BYTES: re_hi, im_hi TF32 (SW128_32B, M-group = 2 frames, LBO 4096),
+            // re_lo, im_lo bf16 (SWIZZLE_128B, MN atom = 64 elements = 4 frames, LBO 4096, 8-row K groups SBO 1024)
+            const uint64_t d_rh = make_desc(a2 + 0, 4096, 512, 1), d_ih = make_desc(a2 + 16384, 4096, 512, 1);
+            const uint64_t d_rl = make_desc(a2 + 32768, 4096, 1024, 2), d_il = make_desc(a2 + 40960, 4096, 1024, 2);
             const uint64_t d_ch = make_desc(c_hi, 512, 128, 0), d_cl = make_desc(c_lo, 512, 128, 0);
             const uint64_t d_sh = make_desc(s_hi, 512, 128, 0), d_sl = make_desc(s_lo, 512, 128, 0);
+            const uint32_t cb = smem_u32(csb_s);
+            const uint64_t d_cb = make_desc(cb, 512, 128, 0), d_sb = make_desc(cb + 2048, 512, 128, 0);
+            // D = F32, A = B = BF16, A MN-major, B K-major, N = 32, M = 128 (kind::f16, K = 16 per instruction)
+            const uint32_t idescb = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idescbn = idescb | (1u << 13);
             // stage 1 of unit `uu` (0 / 1) of the staged tile into D1 slot uu
             auto issue_s1 = [&](int uu) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -214,30 +237,37 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
                 }
                 mma_commit(s1_done + uu);
             };
-            // stage 2 of the unit whose A operand sits in a2_s into D2 slot uu
+            // stage 2 of unit uu (A operand set uu) into D2 slot uu.  hi.hi and hi.lo products in TF32 (K = 8 per MMA), the
+            // lo.hi products in bf16 (K = 16 per MMA): the lo parts are 2^-12 of the values, 8 bits of them are plenty.
             auto issue_s2 = [&](int uu) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (p.ablate & 4) { mma_commit(s2_done + uu); return; }
                 const uint32_t dre = tmem + (uint32_t)(128 + uu * 64), dim = dre + 32;
+                const uint64_t bo = (uint64_t)((uint32_t)uu * (TCM_A2_BYTES / 16));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint64_t ko = (uint64_t)(j * 64);
-                    const uint64_t rh = d_rh + ko, rl = d_rl + ko, ih = d_ih + ko, il = d_il + ko;
+                    const uint64_t rh = d_rh + bo + ko, ih = d_ih + bo + ko;
                     const uint64_t ch = d_ch + ko, cl = d_cl + ko, sh = d_sh + ko, sl = d_sl + ko;
                     // D_re += A_re C + A_im S
-                    if (j == 0) mma_tf32_c<false>(dre, rl, ch, idesc2); else mma_tf32_c<true>(dre, rl, ch, idesc2);
-                    mma_tf32_c<true>(dre, rh, cl, idesc2);
+                    if (j == 0) mma_tf32_c<false>(dre, rh, cl, idesc2); else mma_tf32_c<true>(dre, rh, cl, idesc2);
                     mma_tf32_c<true>(dre, rh, ch, idesc2);
-                    mma_tf32_c<true>(dre, il, sh, idesc2);
                     mma_tf32_c<true>(dre, ih, sl, idesc2);
                     mma_tf32_c<true>(dre, ih, sh, idesc2);
                     // D_im += A_im C - A_re S
-                    if (j == 0) mma_tf32_c<false>(dim, il, ch, idesc2); else mma_tf32_c<true>(dim, il, ch, idesc2);
-                    mma_tf32_c<true>(dim, ih, cl, idesc2);
+                    if (j == 0) mma_tf32_c<false>(dim, ih, cl, idesc2); else mma_tf32_c<true>(dim, ih, cl, idesc2);
                     mma_tf32_c<true>(dim, ih, ch, idesc2);
-                    mma_tf32_c<true>(dim, rl, sh, idesc2n);
                     mma_tf32_c<true>(dim, rh, sl, idesc2n);
                     mma_tf32_c<true>(dim, rh, sh, idesc2n);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint64_t ka = (uint64_t)(j * 128), kb = (uint64_t)(j * 64);   // 16 K rows = 2048 B of A, 2 K chunks = 1024 B of B
+                    const uint64_t rl = d_rl + bo + ka, il = d_il + bo + ka;
+                    mma_bf16(dre, rl, d_cb + kb, idescb);
+                    mma_bf16(dre, il, d_sb + kb, idescb);
+                    mma_bf16(dim, il, d_cb + kb, idescb);
+                    mma_bf16(dim, rl, d_sb + kb, idescbn);
                 }
                 mma_commit(s2_done + uu);
             };
@@ -250,7 +280,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
                 const bool has_next = tile + (int)gridDim.x < n_tiles;
                 const uint32_t pk = (uint32_t)(k & 1), pk1 = (uint32_t)((k - 1) & 1);
-                bar_wait(a2_ready, 0u);                           // unit 0: the (2k)-th completion
+                bar_wait(a2_ready + 0, pk);
                 if (k > 0) bar_wait(d2_free + 0, pk1);
                 issue_s2(0);
                 if (has_next) {
@@ -258,7 +288,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
                     bar_wait(d1_free + 0, pk);                    // X has read D1 slot 0 of tile k
                     issue_s1(0);
                 }
-                bar_wait(a2_ready, 1u);                           // unit 1: the (2k+1)-th completion
+                bar_wait(a2_ready + 1, pk);
                 if (k > 0) bar_wait(d2_free + 1, pk1);
                 issue_s2(1);
                 if (has_next) {
@@ -292,6 +322,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
         // Every thread owns the same 4-element groups i = 4 (tid + 256 it) in every alignment mode, so a thread that is
         // already copying the next tile never touches raw_s elements another thread has not split yet.
         auto prefetch = [&](const float* xsig, long long s0) {
+            if (p.ablate & 16) return;
             const unsigned al = (unsigned)((reinterpret_cast<uintptr_t>(xsig) + (uintptr_t)(s0 * 4)) >> 2) & 3u;
             pmode = (al == 0) ? 4 : ((al & 1u) == 0 ? 2 : 1);
 #pragma unroll
@@ -313,6 +344,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         auto commit_stage = [&]() {
+            if (p.ablate & 16) { bar_arrive(smp_ready); return; }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
             for (int it = 0; it < 5; ++it) {
@@ -337,7 +369,8 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
         auto between_compute = [&](int uu) {
             const int n2 = lane;
             uint32_t sv[32];
-            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(uu * 64 + (warp >> 2) * 32), sv);
+            if (p.ablate & 64) { for (int i = 0; i < 32; ++i) sv[i] = (uint32_t)(lane + i); }
+            else tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(uu * 64 + (warp >> 2) * 32), sv);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(d1_free + uu);                          // D1 slot uu may be overwritten by the next tile's stage 1
             if (p.ablate & 2) { for (int i = 0; i < 16; ++i) { tre[i] = __uint_as_float(sv[i]); tim[i] = __uint_as_float(sv[16 + i]); } return; }
@@ -372,23 +405,36 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
             y0v = y;
             mag0v = kb_sqrt(cnorm(y));
         };
-        // part 2 (after the A operand buffer and the mag0 slot are free): split, store, signal the issuer
+        // part 2 (after A operand set uu and the mag0 slot are free): split, store, signal the issuer
         auto between_store = [&](int uu, int t0, int sig) {
             const int n2 = lane, fl = warp;
-            const uint32_t rowb = (uint32_t)((fl >> 1) * 4096 + n2 * 128);
+            if (p.ablate & 128) { bar_arrive(a2_ready + uu); return; }
+            char* set = a2_s + uu * TCM_A2_BYTES;
+            const uint32_t rowh = (uint32_t)((fl >> 1) * 4096 + n2 * 128);     // TF32 hi parts: M-group = frame pair
+            const uint32_t rowl = (uint32_t)((fl >> 2) * 4096 + n2 * 128);     // bf16 lo parts: MN atom = 4 frames x 16
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint32_t unit = (uint32_t)((fl & 1) * 2 + (i >> 1));
-                const uint32_t o = rowb + (((unit ^ ((uint32_t)n2 & 3u)) << 5) | (uint32_t)((i & 1) << 4));
-                float4 rh, rl, ih, il;
+                const uint32_t o = rowh + (((unit ^ ((uint32_t)n2 & 3u)) << 5) | (uint32_t)((i & 1) << 4));
+                float4 rh, ih;
                 rh.x = tf32_rn(tre[4 * i]); rh.y = tf32_rn(tre[4 * i + 1]); rh.z = tf32_rn(tre[4 * i + 2]); rh.w = tf32_rn(tre[4 * i + 3]);
-                rl.x = tre[4 * i] - rh.x; rl.y = tre[4 * i + 1] - rh.y; rl.z = tre[4 * i + 2] - rh.z; rl.w = tre[4 * i + 3] - rh.w;
                 ih.x = tf32_rn(tim[4 * i]); ih.y = tf32_rn(tim[4 * i + 1]); ih.z = tf32_rn(tim[4 * i + 2]); ih.w = tf32_rn(tim[4 * i + 3]);
-                il.x = tim[4 * i] - ih.x; il.y = tim[4 * i + 1] - ih.y; il.z = tim[4 * i + 2] - ih.z; il.w = tim[4 * i + 3] - ih.w;
-                *reinterpret_cast<float4*>(a2_s + 0 * 16384 + o) = rh;
-                *reinterpret_cast<float4*>(a2_s + 1 * 16384 + o) = rl;
-                *reinterpret_cast<float4*>(a2_s + 2 * 16384 + o) = ih;
-                *reinterpret_cast<float4*>(a2_s + 3 * 16384 + o) = il;
+                *reinterpret_cast<float4*>(set + o) = rh;
+                *reinterpret_cast<float4*>(set + 16384 + o) = ih;
+                tre[4 * i] -= rh.x; tre[4 * i + 1] -= rh.y; tre[4 * i + 2] -= rh.z; tre[4 * i + 3] -= rh.w;   // exact remainders
+                tim[4 * i] -= ih.x; tim[4 * i + 1] -= ih.y; tim[4 * i + 2] -= ih.z; tim[4 * i + 3] -= ih.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {                                      // 8 bf16 = one 16-byte chunk per store
+                const uint32_t chunk = (uint32_t)((fl & 3) * 2 + i);
+                const uint32_t o = rowl + ((chunk ^ ((uint32_t)n2 & 7u)) << 4);
+                uint4 rl, il;
+                rl.x = bf16x2(tre[8 * i], tre[8 * i + 1]); rl.y = bf16x2(tre[8 * i + 2], tre[8 * i + 3]);
+                rl.z = bf16x2(tre[8 * i + 4], tre[8 * i + 5]); rl.w = bf16x2(tre[8 * i + 6], tre[8 * i + 7]);
+                il.x = bf16x2(tim[8 * i], tim[8 * i + 1]); il.y = bf16x2(tim[8 * i + 2], tim[8 * i + 3]);
+                il.z = bf16x2(tim[8 * i + 4], tim[8 * i + 5]); il.w = bf16x2(tim[8 * i + 6], tim[8 * i + 7]);
+                *reinterpret_cast<uint4*>(set + 32768 + o) = rl;
+                *reinterpret_cast<uint4*>(set + 40960 + o) = il;
             }
             const int k2 = brev5(lane);
             if (k2 <= 16) {
@@ -398,8 +444,8 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
                     if (t < p.T) p.dbg[((long long)sig * p.T + t) * 513 + 32 * k2] = make_float2(y0v.re, y0v.im);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A operand: generic stores -> async proxy
-            bar_arrive(a2_ready);
+            if (!(p.ablate & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A operand: generic stores -> async proxy
+            bar_arrive(a2_ready + uu);
         };
 
         // ---- tile loop (per thread, no barrier among the X warps) -----------------------------------------------------------
@@ -423,17 +469,19 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) kb_tc_mel_kernel(const __grid_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             between_compute(0);
             if (k > 0) {
-                bar_wait(s2_done + 1, pk1);                     // stage 2 of the previous unit has read the A buffer
+                bar_wait(s2_done + 0, pk1);                     // stage 2 of unit 0 of the previous tile has read operand set 0
                 bar_wait(d2_free + 0, pk1);                     // Y has read mag0 slot 0 of the previous tile
             }
             between_store(0, t0c, sigc);
             // ---- unit 1 ----
             bar_wait(s1_done + 1, pk);                          // both stage-1 GEMMs of the tile are done: hi_s / lo_s are free
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (has_next) commit_stage();                       // early: the issuer can start the next tile's stage 1
             between_compute(1);
-            if (has_next) commit_stage();
-            bar_wait(s2_done + 0, pk);
-            if (k > 0) bar_wait(d2_free + 1, pk1);
+            if (k > 0) {
+                bar_wait(s2_done + 1, pk1);
+                bar_wait(d2_free + 1, pk1);
+            }
             between_store(1, t0c, sigc);
         }
     } else {

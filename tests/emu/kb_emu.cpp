@@ -124,6 +124,12 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     p.bands = fb ? bands.data() : nullptr; p.fbw = fb ? fbw.data() : nullptr; p.n_bands = fb ? n_bands : 0;
     p.n_fbw = fb ? (int)fbw.size() : 0;
     if (fb) { p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
+    std::vector<kb_i2> bd; std::vector<int> bg;
+    if (fb && (fb_mma & 2)) {          // bit 1: two-level band-descriptor walk of the chunk lists
+        kb_make_fb_band_desc(cm, cg, 32, bd, bg);
+        p.fb_bands = 1; p.bd = bd.data(); p.bg = bg.data(); p.n_bd = (int)bd.size();
+    }
+    fb_mma &= 1;
     std::vector<kb_f4> mw; std::vector<kb_i2> ms; std::vector<int> mg;
     if (fb && fb_mma) {
         kb_make_fb_mma(fb, n_freq, n_bands, mw, ms, mg);

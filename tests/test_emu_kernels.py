@@ -61,6 +61,9 @@ def test_emu_mel_and_db(n_fft, hop, n_mels, sr, TF, nw, fmt):
     ref = O.melspectrogram_layer(x, **kw)
     out, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw)
     assert nerr(out, ref) < 1e-6
+    # two-level walk over band descriptors: the same sums in the same order -> bit-identical
+    out2, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw, fb_mma=2)
+    assert np.array_equal(out, out2)
     refdb = O.melspectrogram_layer(x, return_decibel=True, db_dynamic_range=1e9, **kw)
     outdb, imax = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB_DB, fmt, fmt, fb=fb, TF=TF, n_warps=nw)
     assert np.abs(outdb - refdb).max() < 5e-5
