@@ -995,7 +995,9 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         p.cw = fb->cw; p.cm = fb->cm; p.cg = fb->cg; p.n_chunks = fb->n_chunks;
         p.mw = fb->mw; p.ms = fb->ms; p.mg = fb->mg; p.n_msteps = fb->n_msteps;
         p.bd = fb->bd; p.bg = fb->bg; p.n_bd = fb->n_bd;
-        p.fb_bands = (fb->bd && kb_env_int("KAPRE_B200_FBBANDS", 1)) ? 1 : 0;
+        // measured slower than the flat predicated chunk list (0.184 vs 0.1765 ms on cfg2, profiles/r2_small_experiments.md):
+        // the groups of a warp walk bands of different lengths, the flat list is balanced per group.  Off by default.
+        p.fb_bands = (fb->bd && kb_env_int("KAPRE_B200_FBBANDS", 0)) ? 1 : 0;
     }
     if (dbmode) {
         p.amin = db->amin; p.db_mul = db_mul; p.db_sub = db_sub; p.item_max = (unsigned int*)workspace_dev;
