@@ -132,6 +132,11 @@ int kapre_phase(const void* x_complex_dev, float* out_dev, int64_t n, void* stre
 int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_items, int64_t item_size,
                                const kapre_db_cfg* db, void* workspace_dev, void* stream);
 
+/* kapre.ConcatenateFrequencyMap (kapre/time_frequency.py:648-744): contiguous (b, t, f, ch) [channels_last != 0] or
+ * (b, ch, t, f) float32 input -> the same with one more channel holding linspace(0, 1, n_freq) along the frequency axis. */
+int kapre_concat_frequency_map(const float* x_dev, float* out_dev, int64_t batch, int64_t channels, int64_t frames,
+                               int64_t n_freq, int channels_last, void* stream);
+
 /* ---- adjacent layers (SURVEY 8f "next" rows) ------------------------------------------------ */
 /* kapre.Delta (kapre/time_frequency.py:563-644): y[t] = sum_{m=-n..n} m * x[t+m] / (2 sum m^2) along the
  * time axis of a contiguous tensor viewed as (outer, frames, inner); x is extended beyond its ends by

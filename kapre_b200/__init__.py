@@ -16,6 +16,7 @@ from .time_frequency import (  # noqa: E402
     MagnitudeToDecibel,
     ApplyFilterbank,
     Delta,
+    ConcatenateFrequencyMap,
     Layer,
 )
 from .signal import Frame, Energy, LogmelToMFCC  # noqa: E402
@@ -31,7 +32,7 @@ from .composed import (  # noqa: E402
 __all__ = [
     '__version__', 'VERSION', 'backend', 'composed',
     'STFT', 'InverseSTFT', 'Magnitude', 'Phase', 'MagnitudeToDecibel', 'ApplyFilterbank',
-    'Delta', 'Frame', 'Energy', 'LogmelToMFCC', 'Layer', 'Sequential',
+    'Delta', 'ConcatenateFrequencyMap', 'Frame', 'Energy', 'LogmelToMFCC', 'Layer', 'Sequential',
     'get_stft_magnitude_layer', 'get_melspectrogram_layer', 'get_log_frequency_spectrogram_layer',
     'get_perfectly_reconstructing_stft_istft', 'get_stft_mag_phase',
 ]

@@ -219,6 +219,24 @@ __global__ void kb_phase_kernel(const float2* __restrict__ x, float* __restrict_
     }
 }
 
+// kapre.ConcatenateFrequencyMap (kapre/time_frequency.py:648-744): out = concat(x, linspace(0, 1, F) broadcast over
+// (batch, time)) along the channel axis.  One pass: every output element is either a copy or the map value.
+__global__ void kb_concat_freq_map_kernel(const float* __restrict__ x, float* __restrict__ y, long long B, long long C,
+                                          long long T, long long F, int channels_last) {
+    const long long Co = C + 1;
+    const long long total = B * Co * T * F;
+    const float step = F > 1 ? 1.0f / (float)(F - 1) : 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long b, c, t, f;
+        if (channels_last) { c = i % Co; f = (i / Co) % F; t = (i / (Co * F)) % T; b = i / (Co * F * T); }
+        else { f = i % F; t = (i / F) % T; c = (i / (F * T)) % Co; b = i / (F * T * Co); }
+        float v;
+        if (c == C) v = (f == F - 1 && F > 1) ? 1.0f : (float)f * step;      // tf.linspace: exact end point
+        else v = channels_last ? x[((b * T + t) * F + f) * C + c] : x[((b * C + c) * T + t) * F + f];
+        y[i] = v;
+    }
+}
+
 // ---- adjacent layers: Delta / Frame / Energy (element-wise or small-window kernels, HBM-bound) ----
 __device__ __forceinline__ long long kb_pad_index(long long t, long long T, int mode) {
     // index into [0, T) for an out-of-range t under tf.pad's SYMMETRIC (0) / REFLECT (1); -1 = zero (CONSTANT)
@@ -1289,6 +1307,20 @@ int kapre_phase(const void* x_complex_dev, float* out_dev, int64_t n, void* stre
     int grid, rc;
     if ((rc = kb_ew_grid(n, &grid))) return rc;
     kb_phase_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)x_complex_dev, out_dev, n);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+int kapre_concat_frequency_map(const float* x_dev, float* out_dev, int64_t batch, int64_t channels, int64_t frames,
+                               int64_t n_freq, int channels_last, void* stream) {
+    if (batch < 0 || channels < 0 || frames < 0 || n_freq < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    const long long total = (long long)batch * (channels + 1) * frames * n_freq;
+    if (total == 0) return 0;
+    if (!out_dev || (!x_dev && channels > 0)) return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    int grid, rc;
+    if ((rc = kb_ew_grid(total, &grid))) return rc;
+    kb_concat_freq_map_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, out_dev, batch, channels, frames, n_freq, channels_last ? 1 : 0);
     KB_CUDA(cudaGetLastError());
     g_launches++;
     return 0;

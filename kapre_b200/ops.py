@@ -385,6 +385,26 @@ def delta(x: torch.Tensor, win_length: int, mode: str, data_format: str):
     return out
 
 
+@_device_of_first_arg
+def concat_frequency_map(x: torch.Tensor, data_format: str):
+    """kapre.ConcatenateFrequencyMap: (b, t, f, ch) -> (b, t, f, ch + 1) or (b, ch, t, f) -> (b, ch + 1, t, f)."""
+    if not x.is_cuda:
+        raise N.KapreNativeError('concat_frequency_map needs a CUDA tensor')
+    x = x.float().contiguous()
+    if x.dim() != 4:
+        raise ValueError('ConcatenateFrequencyMap expects a 4-D batch, got shape %s' % (tuple(x.shape),))
+    cl = data_format == _CH_LAST_STR
+    if cl:
+        B, T, F, C = x.shape
+        out = torch.empty((B, T, F, C + 1), dtype=torch.float32, device=x.device)
+    else:
+        B, C, T, F = x.shape
+        out = torch.empty((B, C + 1, T, F), dtype=torch.float32, device=x.device)
+    if out.numel():
+        N.check(N.lib().kapre_concat_frequency_map(_ptr(x), _ptr(out), B, C, T, F, int(cl), _stream_ptr()))
+    return out
+
+
 def _frames_for(length, frame_length, hop, pad_end):
     return -(-length // hop) if pad_end else max(0, 1 + (length - frame_length) // hop)
 

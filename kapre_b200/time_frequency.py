@@ -327,3 +327,22 @@ class Delta(Layer):
         return ops.delta(x, self.win_length, self.mode, self.data_format)
 
     _config_fields = (('win_length', 'win_length'), ('mode', 'mode'), ('data_format', 'data_format_original'))
+
+
+@register_keras_serializable(package='Kapre')
+class ConcatenateFrequencyMap(Layer):
+    """Adds a frequency-information channel: ``linspace(0, 1, n_freq)`` along the frequency axis, broadcast over batch
+    and time, concatenated on the channel axis (reference: kapre/time_frequency.py:648-744)."""
+
+    def __init__(self, data_format='default', **kwargs):
+        super().__init__(**kwargs)
+        backend.validate_data_format_str(data_format)
+        data_format = _unwrap_format(data_format)
+        self.data_format_original = data_format
+        self.data_format = _resolve(data_format)
+
+    def call(self, x):
+        return ops.concat_frequency_map(x, self.data_format)
+
+    _config_fields = (('data_format', 'data_format_original'),)
+

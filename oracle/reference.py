@@ -20,7 +20,7 @@ __all__ = [
     'hz_to_mel', 'mel_to_hz', 'filterbank_mel', 'filterbank_log', 'apply_filterbank',
     'magnitude_to_decibel', 'inverse_stft_window', 'inverse_stft_frames', 'istft_layer',
     'melspectrogram_layer', 'stft_magnitude_layer', 'phase', 'stft_mag_phase_layer',
-    'delta', 'frame_layer', 'energy_layer', 'logmel_to_mfcc', 'dft_stage1_32x32',
+    'delta', 'frame_layer', 'energy_layer', 'logmel_to_mfcc', 'dft_stage1_32x32', 'concat_frequency_map',
 ]
 
 CH_FIRST = 'channels_first'
@@ -481,3 +481,22 @@ def dft_stage1_32x32(x, n_fft=1024, hop=256):
     k1 = np.arange(17)[None, :]
     F = np.exp(-2j * np.pi * n1 * k1 / 32.0)                  # (n1, k1)
     return np.einsum('ifab,ak->ifbk', fr, F)                  # (i, f, n2, k1)
+
+
+def concat_frequency_map(x, data_format=CH_DEFAULT):
+    """kapre/time_frequency.py:707-733: one more channel holding linspace(0, 1, n_freq) (float32, as the reference casts it)
+    along the frequency axis of a (b, t, f, ch) / (b, ch, t, f) batch."""
+    x = np.asarray(x)
+    fmt = resolve_data_format(data_format)
+    F = x.shape[2] if fmt == CH_LAST else x.shape[3]
+    # tf.linspace on Python floats is a float32 op (LinSpace kernel): start + step * i in float32, last element = stop
+    step = np.float32(1.0) / np.float32(F - 1) if F > 1 else np.float32(0.0)
+    m = (np.arange(F, dtype=np.float32) * step).astype(np.float32)
+    if F > 1:
+        m[-1] = np.float32(1.0)
+    if fmt == CH_LAST:
+        B, T, _, C = x.shape
+        return np.concatenate([x, np.broadcast_to(m.reshape(1, 1, F, 1), (B, T, F, 1)).astype(x.dtype)], axis=3)
+    B, C, T, _ = x.shape
+    return np.concatenate([x, np.broadcast_to(m.reshape(1, 1, 1, F), (B, 1, T, F)).astype(x.dtype)], axis=1)
+

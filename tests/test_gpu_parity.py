@@ -566,6 +566,26 @@ def test_delta_literal_and_modes(K):
         K.Delta(mode='wrap')
 
 
+@pytest.mark.parametrize('fmt', ['default', 'channels_first', 'channels_last'])
+def test_concatenate_frequency_map(K, fmt):
+    """Mirror of the reference's test (tests/test_time_frequency.py: ConcatenateFrequencyMap): the added channel is
+    linspace(0, 1, n_freq) on the frequency axis, the other channels are untouched; float equality."""
+    rng = np.random.default_rng(4)
+    shape = (2, 3, 7, 33) if fmt == 'channels_first' else (2, 7, 33, 3)
+    x = rng.normal(size=shape).astype(np.float32)
+    layer = K.ConcatenateFrequencyMap(data_format=fmt)
+    got = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.concat_frequency_map(x, fmt)
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got, ref)
+    assert layer.get_config()['data_format'] == fmt
+    # after a spectrogram layer, as in the reference's docstring example
+    seq = K.Sequential([K.STFT(n_fft=256, hop_length=128), K.Magnitude(), K.ConcatenateFrequencyMap()])
+    y = seq(torch.from_numpy(rng.normal(size=(2, 2048, 1)).astype(np.float32)).cuda())
+    assert tuple(y.shape) == (2, 15, 129, 2)
+    np.testing.assert_allclose(y[0, 3, :, 1].cpu().numpy(), np.linspace(0.0, 1.0, 129), atol=1e-7)
+
+
 @pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
 @pytest.mark.parametrize('pad_end', [False, True])
 def test_frame_and_energy(K, fmt, pad_end):

@@ -152,3 +152,15 @@ def test_cpu_port_matches_oracle():
         ref = O.melspectrogram_layer(x, **kw)
         assert y.shape == ref.shape
         assert np.abs(y - ref).max() < 5e-4
+
+
+def test_concat_frequency_map_oracle():
+    """kapre/time_frequency.py:707-733: the extra channel is linspace(0, 1, n_freq) on the frequency axis."""
+    x = np.zeros((2, 5, 9, 3), dtype=np.float32)
+    y = O.concat_frequency_map(x, 'channels_last')
+    assert y.shape == (2, 5, 9, 4)
+    np.testing.assert_allclose(y[1, 2, :, 3], np.linspace(0, 1, 9), atol=1e-7)
+    assert y[..., 3].min() == 0.0 and y[..., 3].max() == 1.0
+    y = O.concat_frequency_map(np.ones((1, 2, 4, 6), np.float32), 'channels_first')
+    assert y.shape == (1, 3, 4, 6) and (y[0, :2] == 1).all()
+    np.testing.assert_allclose(y[0, 2, 3], np.linspace(0, 1, 6), atol=1e-7)
