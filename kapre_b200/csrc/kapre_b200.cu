@@ -459,8 +459,10 @@ struct FwdCfg { int TF, NW, smem, bps; };
 // latency-bound, so resident warps per SM (up to the 16 the 128-register kernel allows) matter
 // most, then larger tiles (less re-staging of the hop overlap).  Filterbank modes keep the
 // tile's magnitudes in the warps' exchange regions, which needs TF == frames per round.
+// `n_sig` signals of `T` frames each: small batches (BASELINE cfg1 is 244 frames) that cannot fill the machine are
+// latency-bound and get their own choice (see below); everything else maximises resident warps.
 static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int mode, int n_bands, int n_chunks,
-                            int fbmma, FwdCfg* out) {
+                            int fbmma, long long n_sig, int T, FwdCfg* out) {
     const int FPW = 32 / Q;
     const bool fb = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     const int force_tf = kb_env_int("KAPRE_B200_TF", 0);
@@ -468,9 +470,9 @@ static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int m
     const int sm_smem = 228 * 1024;
     bool found = false;
     FwdCfg best{};
-    long best_score = -1;
-    const int nws[4] = {2, 4, 8, 16};
-    for (int a = 0; a < 4; ++a) {
+    double best_score = -1.0;
+    const int nws[5] = {1, 2, 4, 8, 16};
+    for (int a = 0; a < 5; ++a) {
         const int NW = nws[a];
         if (force_nw && NW != force_nw) continue;
         if (NW == 16 && !(Q == 32 && fb && !fbmma)) continue;      // only kb_stft_kernel_w16's instantiations
@@ -485,7 +487,21 @@ static bool kb_pick_fwd_cfg(const DevInfo& dev, int Q, int n_fft, int hop, int m
             if (bps > 16 / NW) bps = 16 / NW;                 // 128 registers per thread: 16 warps per SM
             if (bps < 1) continue;
             const int warps = bps * NW;
-            const long score = (long)warps * 1000 + TF * 10 + NW;
+            // throughput score (large problems): resident warps first, then longer tiles (less re-staging of the overlap)
+            double score = (double)warps * 1000.0 + TF * 10.0 + NW;
+            if (n_sig > 0 && T > 0) {
+                const double tiles = (double)n_sig * (double)((T + TF - 1) / TF);
+                const double slots = (double)dev.sm_count * bps;
+                if (tiles < slots) {
+                    // latency regime: all tiles run at once and the call costs one tile (~10 us: table prologue, one FFT round,
+                    // filterbank, copy-out).  Measured on cfg1 (244 frames, profiles/r2_small_batch_latency.txt): 4-warp CTAs 10.3 us,
+                    // 8-, 2- and 1-warp CTAs 12.3 us -- so prefer 4 warps, then one round per tile, then more tiles.
+                    const double rounds = (double)((TF + FR - 1) / FR);
+                    score = 1.0e6 - (NW == 4 ? 0.0 : 500.0) - rounds * 200.0 - (double)TF;
+                } else {
+                    score += 2.0e6;                               // any shape that fills the machine beats one that does not
+                }
+            }
             if (score > best_score) {
                 best_score = score;
                 best = FwdCfg{TF, NW, L.total, bps};
@@ -996,7 +1012,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     // filterbank phase on the tensor pipe (mma.sync 3xTF32) or on the CUDA cores (chunk lists)
     const int fbmma = (fbmode && fb->mw && kb_env_int("KAPRE_B200_FBMMA", KB_FBMMA_DEFAULT)) ? 1 : 0;
     if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0,
-                         fbmode ? (fbmma ? fb->n_msteps : fb->n_chunks) : 0, fbmma, &cfg))
+                         fbmode ? (fbmma ? fb->n_msteps : fb->n_chunks) : 0, fbmma, (long long)B * C, T, &cfg))
         return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
                        plan->n_fft, plan->hop, fbmode ? fb->n_bands : 0);
     KbStftParams p{};

@@ -96,7 +96,7 @@ def test_fuzz_inverse(n_fft, hop_div, frames, C, ifmt, ofmt, nw, seed):
 @settings(**COMMON)
 @given(n_fft=st.sampled_from([256, 512]), hop=st.integers(32, 260), L=st.integers(800, 2600), C=st.integers(1, 4),
        n_mels=st.integers(3, 48), htk=st.booleans(), pad_end=st.booleans(), ifmt=FMT, ofmt=FMT,
-       nw=st.sampled_from([2, 4, 8]), all_channels=st.booleans(), seed=st.integers(0, 10 ** 6))
+       nw=st.sampled_from([1, 2, 4, 8]), all_channels=st.booleans(), seed=st.integers(0, 10 ** 6))
 def test_fuzz_filterbank_modes(n_fft, hop, L, C, n_mels, htk, pad_end, ifmt, ofmt, nw, all_channels, seed):
     """Mel + dB epilogue on both tile kinds: chunk lists for arbitrary band counts, partial rounds, copy-out."""
     fpw = 32 // (n_fft // 64)

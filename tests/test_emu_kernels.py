@@ -48,7 +48,8 @@ def test_emu_staging_paths(dbuf, bulk, L):
 @pytest.mark.parametrize('n_fft,hop,n_mels,sr,TF,nw', [(1024, 256, 128, 22050, 16, 8), (1024, 256, 128, 22050, 8, 4),
                                                         (512, 256, 40, 22050, 16, 4), (2048, 512, 64, 44100, 8, 8),
                                                         (2048, 512, 128, 44100, 4, 4), (256, 64, 20, 16000, 32, 4),
-                                                        (512, 128, 64, 16000, 8, 2), (1024, 256, 80, 16000, 4, 2)])
+                                                        (512, 128, 64, 16000, 8, 2), (1024, 256, 80, 16000, 4, 2),
+                                                        (512, 256, 64, 16000, 4, 1), (1024, 256, 128, 22050, 2, 1)])   # 1-warp CTAs: small batches
 @pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
 def test_emu_mel_and_db(n_fft, hop, n_mels, sr, TF, nw, fmt):
     rng = np.random.default_rng(n_mels)
