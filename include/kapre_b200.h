@@ -137,6 +137,14 @@ int kapre_magnitude_to_decibel(const float* x_dev, float* out_dev, int64_t n_ite
 int kapre_concat_frequency_map(const float* x_dev, float* out_dev, int64_t batch, int64_t channels, int64_t frames,
                                int64_t n_freq, int channels_last, void* stream);
 
+/* kapre.SpecAugment (kapre/augmentation.py:116-326) on a contiguous (batch, frames, n_freq) float32 tensor (depth 1: both data
+ * formats have this memory layout).  `time_masks_dev` / `freq_masks_dev`: (batch, n_masks, 2) int32 (start, width) pairs; an element
+ * whose time (frequency) index lies in [start, start + width] of any mask of its item becomes mask_value.  The pairs are drawn by the
+ * caller (width ~ U{0..param-1}, start ~ U{0..limit-width-1}, as the reference does per item and mask). */
+int kapre_spec_augment(const float* x_dev, float* out_dev, int64_t batch, int64_t frames, int64_t n_freq,
+                       const int* time_masks_dev, int n_time_masks, const int* freq_masks_dev, int n_freq_masks,
+                       float mask_value, void* stream);
+
 /* ---- adjacent layers (SURVEY 8f "next" rows) ------------------------------------------------ */
 /* kapre.Delta (kapre/time_frequency.py:563-644): y[t] = sum_{m=-n..n} m * x[t+m] / (2 sum m^2) along the
  * time axis of a contiguous tensor viewed as (outer, frames, inner); x is extended beyond its ends by

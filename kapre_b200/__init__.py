@@ -20,6 +20,8 @@ from .time_frequency import (  # noqa: E402
     Layer,
 )
 from .signal import Frame, Energy, LogmelToMFCC  # noqa: E402
+from .augmentation import SpecAugment  # noqa: E402
+from . import augmentation  # noqa: E402
 from .composed import (  # noqa: E402
     Sequential,
     get_stft_magnitude_layer,
@@ -32,7 +34,7 @@ from .composed import (  # noqa: E402
 __all__ = [
     '__version__', 'VERSION', 'backend', 'composed',
     'STFT', 'InverseSTFT', 'Magnitude', 'Phase', 'MagnitudeToDecibel', 'ApplyFilterbank',
-    'Delta', 'ConcatenateFrequencyMap', 'Frame', 'Energy', 'LogmelToMFCC', 'Layer', 'Sequential',
+    'Delta', 'ConcatenateFrequencyMap', 'Frame', 'Energy', 'LogmelToMFCC', 'SpecAugment', 'augmentation', 'Layer', 'Sequential',
     'get_stft_magnitude_layer', 'get_melspectrogram_layer', 'get_log_frequency_spectrogram_layer',
     'get_perfectly_reconstructing_stft_istft', 'get_stft_mag_phase',
 ]

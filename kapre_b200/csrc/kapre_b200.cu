@@ -237,6 +237,29 @@ __global__ void kb_concat_freq_map_kernel(const float* __restrict__ x, float* __
     }
 }
 
+// kapre.SpecAugment (kapre/augmentation.py:116-326): per item, every element whose time index lies in one of the item's time
+// masks [start, start + width] or whose frequency index lies in one of its frequency masks is replaced by mask_value
+// (tf.where(mask, mask_value, x) after reduce_any over the masks).  The (start, width) pairs are drawn on the host
+// (the reference draws them with tf.random.uniform per item and mask); depth is 1, so both data formats are (b, t, f).
+__global__ void kb_spec_augment_kernel(const float* __restrict__ x, float* __restrict__ y, long long B, long long T, long long F,
+                                       const int* __restrict__ tmask, int n_t, const int* __restrict__ fmask, int n_f,
+                                       float mask_value) {
+    const long long total = B * T * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i % F, t = (i / F) % T, b = i / (F * T);
+        bool m = false;
+        for (int j = 0; j < n_t; ++j) {
+            const int s0 = tmask[(b * n_t + j) * 2], w = tmask[(b * n_t + j) * 2 + 1];
+            m = m || (t >= s0 && t <= s0 + w);
+        }
+        for (int j = 0; j < n_f; ++j) {
+            const int s0 = fmask[(b * n_f + j) * 2], w = fmask[(b * n_f + j) * 2 + 1];
+            m = m || (f >= s0 && f <= s0 + w);
+        }
+        y[i] = m ? mask_value : x[i];
+    }
+}
+
 // ---- adjacent layers: Delta / Frame / Energy (element-wise or small-window kernels, HBM-bound) ----
 __device__ __forceinline__ long long kb_pad_index(long long t, long long T, int mode) {
     // index into [0, T) for an out-of-range t under tf.pad's SYMMETRIC (0) / REFLECT (1); -1 = zero (CONSTANT)
@@ -1337,6 +1360,23 @@ int kapre_concat_frequency_map(const float* x_dev, float* out_dev, int64_t batch
     int grid, rc;
     if ((rc = kb_ew_grid(total, &grid))) return rc;
     kb_concat_freq_map_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, out_dev, batch, channels, frames, n_freq, channels_last ? 1 : 0);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+int kapre_spec_augment(const float* x_dev, float* out_dev, int64_t batch, int64_t frames, int64_t n_freq,
+                       const int* time_masks_dev, int n_time_masks, const int* freq_masks_dev, int n_freq_masks,
+                       float mask_value, void* stream) {
+    if (batch < 0 || frames < 0 || n_freq < 0 || n_time_masks < 0 || n_freq_masks < 0) return kb_fail(KAPRE_E_INVALID, "negative size");
+    const long long total = (long long)batch * frames * n_freq;
+    if (total == 0) return 0;
+    if (!x_dev || !out_dev || (n_time_masks && !time_masks_dev) || (n_freq_masks && !freq_masks_dev))
+        return kb_fail(KAPRE_E_INVALID, "null data pointer");
+    int grid, rc;
+    if ((rc = kb_ew_grid(total, &grid))) return rc;
+    kb_spec_augment_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, out_dev, batch, frames, n_freq, time_masks_dev,
+                                                                 n_time_masks, freq_masks_dev, n_freq_masks, mask_value);
     KB_CUDA(cudaGetLastError());
     g_launches++;
     return 0;

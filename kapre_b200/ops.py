@@ -405,6 +405,28 @@ def concat_frequency_map(x: torch.Tensor, data_format: str):
     return out
 
 
+@_device_of_first_arg
+def spec_augment(x: torch.Tensor, time_masks: np.ndarray, freq_masks: np.ndarray, mask_value: float, data_format: str):
+    """kapre.SpecAugment with given masks: x (b, t, f, 1) or (b, 1, t, f); masks (b, n, 2) int32 (start, width)."""
+    if not x.is_cuda:
+        raise N.KapreNativeError('spec_augment needs a CUDA tensor')
+    x = x.float().contiguous()
+    if data_format == _CH_LAST_STR:
+        B, T, F, C = x.shape
+    else:
+        B, C, T, F = x.shape
+    if C != 1:
+        raise RuntimeError('SpecAugment does not support spectrograms with depth greater than 1')
+    out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
+    tm = torch.as_tensor(np.ascontiguousarray(time_masks, dtype=np.int32).reshape(B, -1, 2)).to(x.device)
+    fm = torch.as_tensor(np.ascontiguousarray(freq_masks, dtype=np.int32).reshape(B, -1, 2)).to(x.device)
+    N.check(N.lib().kapre_spec_augment(_ptr(x), _ptr(out), B, T, F, _ptr(tm) if tm.numel() else None, tm.shape[1],
+                                       _ptr(fm) if fm.numel() else None, fm.shape[1], ctypes.c_float(mask_value), _stream_ptr()))
+    return out
+
+
 def _frames_for(length, frame_length, hop, pad_end):
     return -(-length // hop) if pad_end else max(0, 1 + (length - frame_length) // hop)
 

@@ -20,7 +20,7 @@ __all__ = [
     'hz_to_mel', 'mel_to_hz', 'filterbank_mel', 'filterbank_log', 'apply_filterbank',
     'magnitude_to_decibel', 'inverse_stft_window', 'inverse_stft_frames', 'istft_layer',
     'melspectrogram_layer', 'stft_magnitude_layer', 'phase', 'stft_mag_phase_layer',
-    'delta', 'frame_layer', 'energy_layer', 'logmel_to_mfcc', 'dft_stage1_32x32', 'concat_frequency_map',
+    'delta', 'frame_layer', 'energy_layer', 'logmel_to_mfcc', 'dft_stage1_32x32', 'concat_frequency_map', 'spec_augment',
 ]
 
 CH_FIRST = 'channels_first'
@@ -499,4 +499,27 @@ def concat_frequency_map(x, data_format=CH_DEFAULT):
         return np.concatenate([x, np.broadcast_to(m.reshape(1, 1, F, 1), (B, T, F, 1)).astype(x.dtype)], axis=3)
     B, C, T, _ = x.shape
     return np.concatenate([x, np.broadcast_to(m.reshape(1, 1, 1, F), (B, 1, T, F)).astype(x.dtype)], axis=1)
+
+
+def spec_augment(x, time_masks, freq_masks, mask_value=0.0, data_format=CH_DEFAULT):
+    """kapre/augmentation.py:205-260 with the random draws given: per item, elements whose time index lies in
+    [start, start + width] of any of its time masks, or whose frequency index lies in such a range of any of its frequency
+    masks, become mask_value.  Masks: (batch, n, 2) integer (start, width)."""
+    x = np.array(x, copy=True)
+    fmt = resolve_data_format(data_format)
+    t_ax, f_ax = (1, 2) if fmt == CH_LAST else (2, 3)
+    T, F = x.shape[t_ax], x.shape[f_ax]
+    for b in range(x.shape[0]):
+        mt = np.zeros(T, dtype=bool)
+        for s0, w in np.asarray(time_masks)[b].reshape(-1, 2):
+            mt |= (np.arange(T) >= s0) & (np.arange(T) <= s0 + w)
+        mf = np.zeros(F, dtype=bool)
+        for s0, w in np.asarray(freq_masks)[b].reshape(-1, 2):
+            mf |= (np.arange(F) >= s0) & (np.arange(F) <= s0 + w)
+        m = mt[:, None] | mf[None, :]
+        if fmt == CH_LAST:
+            x[b][m] = mask_value
+        else:
+            x[b][:, m] = mask_value
+    return x
 

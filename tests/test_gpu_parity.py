@@ -587,6 +587,37 @@ def test_concatenate_frequency_map(K, fmt):
 
 
 @pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_spec_augment(K, fmt):
+    """Mirror of the reference's SpecAugment tests (tests/test_augmentation.py): identity unless training=True, depth must be 1,
+    masked elements equal mask_value and every other element is untouched; the applied masks (drawn on the host) reproduce
+    the output through the oracle exactly; widths / starts stay inside the ranges tf.random.uniform would give."""
+    rng = np.random.default_rng(8)
+    shape = (5, 1, 40, 30) if fmt == 'channels_first' else (5, 40, 30, 1)
+    x = rng.normal(size=shape).astype(np.float32) + 10.0
+    layer = K.SpecAugment(freq_mask_param=5, time_mask_param=10, n_freq_masks=3, n_time_masks=2, mask_value=-1.0,
+                          data_format=fmt, seed=3)
+    xt = torch.from_numpy(x).cuda()
+    assert layer(xt) is xt and layer(xt, training=False) is xt
+    y = layer(xt, training=True).cpu().numpy()
+    tm, fm = layer.last_masks
+    assert tm.shape == (5, 2, 2) and fm.shape == (5, 3, 2)
+    assert (tm[..., 1] >= 0).all() and (tm[..., 1] < 10).all() and (tm[..., 0] >= 0).all() and (tm[..., 0] + tm[..., 1] < 40).all()
+    assert (fm[..., 1] >= 0).all() and (fm[..., 1] < 5).all() and (fm[..., 0] + fm[..., 1] < 30).all()
+    ref = O.spec_augment(x, tm, fm, -1.0, fmt)
+    np.testing.assert_array_equal(y, ref)
+    assert (y == -1.0).any() and (y[y != -1.0] > 0).all()
+    cfg = layer.get_config()
+    assert cfg['freq_mask_param'] == 5 and cfg['n_time_masks'] == 2 and cfg['data_format'] == fmt
+    with pytest.raises(RuntimeError):
+        K.SpecAugment(freq_mask_param=0, time_mask_param=3)
+    with pytest.raises(RuntimeError):
+        bad = torch.zeros((2, 2, 40, 30) if fmt == 'channels_first' else (2, 40, 30, 2), device='cuda')
+        layer(bad, training=True)
+    with pytest.raises(ValueError):
+        K.SpecAugment(freq_mask_param=50, time_mask_param=3, data_format=fmt)(xt, training=True)
+
+
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
 @pytest.mark.parametrize('pad_end', [False, True])
 def test_frame_and_energy(K, fmt, pad_end):
     """Mirrors of tests/test_signal.py (Frame / Energy) against the oracle."""

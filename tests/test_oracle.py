@@ -164,3 +164,20 @@ def test_concat_frequency_map_oracle():
     y = O.concat_frequency_map(np.ones((1, 2, 4, 6), np.float32), 'channels_first')
     assert y.shape == (1, 3, 4, 6) and (y[0, :2] == 1).all()
     np.testing.assert_allclose(y[0, 2, 3], np.linspace(0, 1, 6), atol=1e-7)
+
+
+def test_spec_augment_oracle_and_mask_sampler():
+    """kapre/augmentation.py:205-208: width in [0, param), start in [0, limit - width): the sampler's ranges, and the oracle's
+    inclusive [start, start + width] masking."""
+    import kapre_b200.augmentation as A
+    rng = np.random.default_rng(0)
+    m = A.draw_masks(rng, 2000, 3, 7, 20)
+    assert m.shape == (2000, 3, 2) and m.dtype == np.int32
+    assert set(np.unique(m[..., 1])) == set(range(7))
+    assert (m[..., 0] >= 0).all() and (m[..., 0] + m[..., 1] <= 19).all()
+    assert m[..., 0][m[..., 1] == 0].max() == 19          # a width-0 mask may start at the last index
+    x = np.ones((1, 6, 5, 1), np.float32)
+    y = O.spec_augment(x, [[[1, 1]]], [[[4, 0]]], 9.0, 'channels_last')
+    assert (y[0, 1:3] == 9).all() and (y[0, :, 4] == 9).all() and y[0, 0, 0, 0] == 1 and y[0, 3, 3, 0] == 1
+    with pytest.raises(ValueError):
+        A.draw_masks(rng, 1, 1, 30, 20)
