@@ -235,3 +235,288 @@ __device__ __forceinline__ void kb_istft_cta(const KbIstftParams& p, char* smem,
         KB_SYNC_CTA;
     }
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Streaming formulation (round 2).  A tile owns `seg` consecutive output hops of one signal and walks
+// them in rounds of FR = n_warps * FPW consecutive frames.  Per round every warp inverse-transforms its
+// frames exactly as above but leaves the windowed time-domain frame in its OWN exchange region (the
+// frame's 2P floats fit the (P + Q) complex slots its spectrum occupied); after one CTA barrier all
+// threads gather-sum the <= R frames that cover each output sample, add the carry of the previous round
+// (the win - hop samples past the last complete hop), store the FR complete hops and write the new
+// carry.  Against the class-ordered overlap-add above: no (TFc * hop + win) accumulation buffer (37 KB
+// at n_fft 1024 -- it capped the residency at two 4-warp CTAs per SM), one shared-memory store + <= R
+// loads per sample instead of R read-modify-writes, R - 1 halo frames per `seg` hops instead of per 29.
+struct KbIstft2Smem {
+    int dual, twp, twn, carry, ex, total;
+    int carry_len;            // floats per carry buffer (two of them, ping-pong)
+};
+
+KB_HD KbIstft2Smem kb_istft2_smem_layout(int Q, int n_fft, int hop, int win, int n_warps) {
+    KbIstft2Smem s;
+    const int P = 32 * Q;
+    int off = 0;
+    s.dual = off; off += kb_align16((n_fft + 4) * 4);      // zero beyond win: samples past win_length vanish in the frame
+    s.twp = off;  off += kb_align16(Q * 33 * 8);
+    s.twn = off;  off += kb_align16((P / 2) * 8);
+    s.carry_len = win > hop ? ((win - hop + 3) & ~3) : 4;
+    s.carry = off; off += 2 * kb_align16(s.carry_len * 4);
+    s.ex = off;   off += n_warps * (32 * 33 * 8);
+    s.total = off;
+    return s;
+}
+
+KB_HD int kb_istft2_tiles(int T, int hop, int win_length, int seg) {
+    const long long out_len = (long long)(T - 1) * hop + win_length;
+    const long long hops = (out_len + hop - 1) / hop;
+    return (int)((hops + seg - 1) / seg);
+}
+
+template <int Q>
+#if defined(KB_HOST_EMU)
+inline void kb_istft2_cta(const KbIstftParams& p, char* smem, int cta, int n_cta)
+#else
+__device__ __forceinline__ void kb_istft2_cta(const KbIstftParams& p, char* smem, int cta, int n_cta)
+#endif
+{
+    constexpr int P = 32 * Q;
+    constexpr int FPW = 32 / Q;
+    constexpr int ZSTR = P + Q;
+    constexpr int EXW = 32 * 33;
+    const int NW = p.n_warps;
+    const int kb_nt = NW * 32;
+    (void)kb_nt;
+    const int H = p.hop, win = p.win, Rm1 = p.R - 1, seg = p.seg;
+    const KbIstft2Smem L = kb_istft2_smem_layout(Q, p.n_fft, H, win, NW);
+    float* dual_s = reinterpret_cast<float*>(smem + L.dual);
+    cpx* twp_s = reinterpret_cast<cpx*>(smem + L.twp);
+    cpx* twn_s = reinterpret_cast<cpx*>(smem + L.twn);
+    float* carry_s = reinterpret_cast<float*>(smem + L.carry);
+    const int carry_stride = kb_align16(L.carry_len * 4) / 4;
+    cpx* ex_s = reinterpret_cast<cpx*>(smem + L.ex);
+    const int FR = NW * FPW;                       // frames per round
+    const int clen = win > H ? win - H : 0;        // live carry samples
+    const int n_tiles = p.B * p.C * p.n_tiles_t;
+    const int n_need = seg + Rm1;                  // frames a tile transforms (incl. the R - 1 halo frames in front)
+    const int n_rounds = (n_need + FR - 1) / FR;
+    const bool vec4 = (H & 3) == 0 && (win & 3) == 0;
+
+#if defined(KB_HOST_EMU)
+    std::vector<KbThreadRegs> kb_regs(kb_nt);
+#else
+    KbThreadRegs kb_regs;
+#endif
+
+    KB_PHASE_BEGIN
+        (void)R;
+        for (int i = tid; i < p.n_fft + 4; i += kb_nt) dual_s[i] = i < win ? p.dual[i] : 0.0f;
+        for (int i = tid; i < Q * 33; i += kb_nt) { float2 t = p.twp[i]; twp_s[i] = cmake(t.x, t.y); }
+        for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
+    KB_PHASE_END
+    KB_SYNC_CTA;
+
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+        const int sig = tile / p.n_tiles_t;
+        const int tt = tile - sig * p.n_tiles_t;
+        const int b = sig / p.C, c = sig - b * p.C;
+        const int h0 = tt * seg;                 // first output hop of the tile
+        const int tf0 = h0 - Rm1;                // first (possibly negative) frame transformed
+        const float2* Xsig = p.X + (long long)b * p.x_sb + (long long)c * p.x_sc;
+        float* ysig = p.y + (long long)b * p.y_sb + (long long)c * p.y_sc;
+        const long long s_lo = (long long)h0 * H;
+        long long s_hi = s_lo + (long long)seg * H;
+        if (s_hi > p.out_len) s_hi = p.out_len;
+
+        KB_PHASE_BEGIN
+            (void)R;
+            for (int i = tid; i < L.carry_len; i += kb_nt) carry_s[i] = 0.0f;
+        KB_PHASE_END
+        // (the first read of the carry is behind the round's CTA barrier)
+
+        for (int round = 0; round < n_rounds; ++round) {
+            const int f_base = round * FR;       // index of the round's first frame within the tile
+            const int tfr = tf0 + f_base;        // its frame number
+            // ---- phase 1: X[k], X[P-k] -> conj(2 Z[k]), conj(2 Z[P-k]) in natural order ----
+            KB_PHASE_BEGIN
+                (void)R;
+                const int warp = tid >> 5, lane = tid & 31;
+                // the frame's 16 bin pairs per lane go through registers in two batches of 8 (all 16 in flight at once cost
+                // 64 registers and, under the 128-register budget of four CTAs per SM, spills)
+                constexpr int HQ = Q / 2;
+                bool live[FPW];
+                const float2* Xf[FPW];
+#pragma unroll
+                for (int gg = 0; gg < FPW; ++gg) {
+                    const int fl = warp * FPW + gg;
+                    const int t = tfr + fl;
+                    live[gg] = f_base + fl < n_need && t >= 0 && t < p.T;
+                    Xf[gg] = Xsig + (long long)(live[gg] ? t : 0) * p.x_st;
+                }
+#pragma unroll
+                for (int cch = 0; cch < 2; ++cch) {
+                    float2 xa[8], xb[8];
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const int e = cch * 8 + e8, gg = e / HQ, i = e % HQ;
+                        if (live[gg]) {
+                            const int k = lane + 32 * i;
+                            xa[e8] = Xf[gg][(long long)k * p.x_sk];
+                            xb[e8] = Xf[gg][(long long)(P - k) * p.x_sk];
+                        }
+                    }
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const int e = cch * 8 + e8, gg = e / HQ, i = e % HQ;
+                        if (!live[gg]) continue;
+                        cpx* zf = ex_s + warp * EXW + gg * ZSTR;
+                        const int k = lane + 32 * i;
+                        float2 a = xa[e8];
+                        float2 bq = xb[e8];
+                        if (k == 0) { a.y = 0.0f; bq.y = 0.0f; }  // C2R ignores Im of DC / Nyquist
+                        const cpx W = twn_s[k];
+                        const float Er = a.x + bq.x, Ei = a.y - bq.y;
+                        const float dr = a.x - bq.x, di = a.y + bq.y;
+                        const float Or = W.re * dr + W.im * di;
+                        const float Oi = W.re * di - W.im * dr;
+                        zf[k] = cmake(Er - Oi, -(Ei + Or));
+                        if (k != 0) zf[P - k] = cmake(Er + Oi, Ei - Or);
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < FPW; ++gg)
+                    if (live[gg] && lane == 0) {
+                        const float2 xm = Xf[gg][(long long)(P / 2) * p.x_sk];
+                        ex_s[warp * EXW + gg * ZSTR + P / 2] = cmake(2.0f * xm.x, 2.0f * xm.y);
+                    }
+            KB_PHASE_END
+            KB_SYNC_WARP;
+            // ---- phase 2a: strided gather of the packed sequence into registers ----------
+            KB_PHASE_BEGIN
+                const int warp = tid >> 5, lane = tid & 31;
+                const int g = lane / Q, q = lane % Q;
+                const int fl = warp * FPW + g;
+                const int t = tfr + fl;
+                if (f_base + fl < n_need && t >= 0 && t < p.T) {
+                    const cpx* zf = ex_s + warp * EXW + g * ZSTR;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) R.v[j] = zf[q + Q * j];
+                }
+            KB_PHASE_END
+            KB_SYNC_WARP;
+            // ---- phase 2b: 32-point DFTs, twiddle, transpose-store ------------------------
+            KB_PHASE_BEGIN
+                const int warp = tid >> 5, lane = tid & 31;
+                const int g = lane / Q, q = lane % Q;
+                const int fl = warp * FPW + g;
+                const int t = tfr + fl;
+                if (f_base + fl < n_need && t >= 0 && t < p.T) {
+                    kb_fft_dif<32>(R.v);
+                    cpx* ex = ex_s + warp * EXW + (g * Q + q) * 33;
+                    const cpx* tw = twp_s + q * 33;
+                    ex[0] = R.v[0];
+#pragma unroll
+                    for (int k1 = 1; k1 < 32; ++k1) ex[k1] = cmul(R.v[kb_brev<32>(k1)], tw[k1]);
+                }
+            KB_PHASE_END
+            KB_SYNC_WARP;
+            // ---- phase 3a: column gather --------------------------------------------------
+            KB_PHASE_BEGIN
+                const int warp = tid >> 5, lane = tid & 31;
+                const int g = lane / Q, q = lane % Q;
+                const int fl = warp * FPW + g;
+                const int t = tfr + fl;
+                if (f_base + fl < n_need && t >= 0 && t < p.T) {
+                    const cpx* ex = ex_s + warp * EXW + (g * Q) * 33;
+#pragma unroll
+                    for (int i = 0; i < FPW; ++i) {
+                        const int k1 = q + Q * i;
+#pragma unroll
+                        for (int q2 = 0; q2 < Q; ++q2) R.v[i * Q + q2] = ex[q2 * 33 + k1];
+                    }
+                }
+            KB_PHASE_END
+            KB_SYNC_WARP;    // every lane has its columns: the frame's slots may now take the time-domain samples
+            // ---- phase 3b: Q-point DFTs, dual window, frame left in place (natural sample order) ----
+            KB_PHASE_BEGIN
+                const int warp = tid >> 5, lane = tid & 31;
+                const int g = lane / Q, q = lane % Q;
+                const int fl = warp * FPW + g;
+                const int t = tfr + fl;
+                if (f_base + fl < n_need && t >= 0 && t < p.T) {
+                    cpx* fr = ex_s + warp * EXW + g * ZSTR;
+                    const cpx* d2 = reinterpret_cast<const cpx*>(dual_s);
+#pragma unroll
+                    for (int i = 0; i < FPW; ++i) {
+                        kb_fft_dif<Q>(R.v + i * Q);
+                        const int k1 = q + Q * i;
+#pragma unroll
+                        for (int k2 = 0; k2 < Q; ++k2) {
+                            const int cidx = k1 + 32 * k2;       // samples 2 cidx, 2 cidx + 1
+                            fr[cidx] = cmul_elem(R.v[i * Q + kb_brev<Q>(k2)], d2[cidx]);
+                        }
+                    }
+                }
+            KB_PHASE_END
+            KB_SYNC_CTA;
+            // ---- phase 4: gather-sum the frames over each sample, store FR hops, write the new carry ----
+            KB_PHASE_BEGIN
+                (void)R;
+                const float* cin = carry_s + (round & 1) * carry_stride;
+                float* cout = carry_s + ((round & 1) ^ 1) * carry_stride;
+                const int E = FR * H + clen;             // samples touched by this round
+                // frames of this round that exist
+                int fv_lo = -tfr; if (fv_lo < 0) fv_lo = 0;
+                int fv_hi = FR - 1;
+                if (fv_hi > p.T - 1 - tfr) fv_hi = p.T - 1 - tfr;
+                if (fv_hi > n_need - 1 - f_base) fv_hi = n_need - 1 - f_base;
+                const long long s0 = (long long)tfr * H; // sample number of u = 0
+                const bool yvec = vec4 && p.y_sl == 1 && ((reinterpret_cast<uintptr_t>(ysig) & 15) == 0);
+                if (vec4) {
+                    for (int u = tid * 4; u < E; u += kb_nt * 4) {
+                        kb_f4 v;
+                        if (u < clen) v = *reinterpret_cast<const kb_f4*>(cin + u);
+                        else { v.x = 0.0f; v.y = 0.0f; v.z = 0.0f; v.w = 0.0f; }
+                        int f_hi = u / H; if (f_hi > fv_hi) f_hi = fv_hi;
+                        int f_lo = u - win + H; f_lo = f_lo > 0 ? f_lo / H : 0; if (f_lo < fv_lo) f_lo = fv_lo;
+                        for (int f = f_lo; f <= f_hi; ++f) {
+                            const float* fb = reinterpret_cast<const float*>(ex_s + (f / FPW) * EXW + (f % FPW) * ZSTR);
+                            const kb_f4 a = *reinterpret_cast<const kb_f4*>(fb + (u - f * H));
+                            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                        }
+                        if (u < FR * H) {
+                            const long long s = s0 + u;
+                            if (s >= s_lo && s + 3 < s_hi && yvec) *reinterpret_cast<kb_f4*>(ysig + s) = v;
+                            else {
+                                if (s >= s_lo && s < s_hi) ysig[s * p.y_sl] = v.x;
+                                if (s + 1 >= s_lo && s + 1 < s_hi) ysig[(s + 1) * p.y_sl] = v.y;
+                                if (s + 2 >= s_lo && s + 2 < s_hi) ysig[(s + 2) * p.y_sl] = v.z;
+                                if (s + 3 >= s_lo && s + 3 < s_hi) ysig[(s + 3) * p.y_sl] = v.w;
+                            }
+                        } else {
+                            *reinterpret_cast<kb_f4*>(cout + (u - FR * H)) = v;
+                        }
+                    }
+                } else {
+                    for (int u = tid; u < E; u += kb_nt) {
+                        float v = u < clen ? cin[u] : 0.0f;
+                        int f_hi = u / H; if (f_hi > fv_hi) f_hi = fv_hi;
+                        int f_lo = u - win + H; f_lo = f_lo > 0 ? f_lo / H : 0; if (f_lo < fv_lo) f_lo = fv_lo;
+                        for (int f = f_lo; f <= f_hi; ++f) {
+                            const float* fb = reinterpret_cast<const float*>(ex_s + (f / FPW) * EXW + (f % FPW) * ZSTR);
+                            v += fb[u - f * H];
+                        }
+                        if (u < FR * H) {
+                            const long long s = s0 + u;
+                            if (s >= s_lo && s < s_hi) ysig[s * p.y_sl] = v;
+                        } else {
+                            cout[u - FR * H] = v;
+                        }
+                    }
+                }
+            KB_PHASE_END
+            KB_SYNC_CTA;
+        }
+        // an odd number of rounds leaves the live carry in buffer 1; the next tile zeroes buffer 0 and starts
+        // with round 0 reading buffer 0 -- nothing carries over between tiles
+    }
+}

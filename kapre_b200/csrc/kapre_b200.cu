@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_dft_kernel(const __grid_
     kb_dft_cta(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
-__global__ void __launch_bounds__(KB_MAX_WARPS * 32) kb_mr_kernel(const __grid_constant__ KbMrParams p) {
+__global__ void __launch_bounds__(512) kb_mr_kernel(const __grid_constant__ KbMrParams p) {
     extern __shared__ __align__(16) char kb_smem[];
     kb_mr_cta(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
@@ -608,6 +608,23 @@ static int kb_launch_stft(const KbStftParams& p, int grid, int smem, cudaStream_
 }
 
 template <int Q>
+__global__ void __launch_bounds__(KB_ISTFT_MAX_WARPS * 32, 4) kb_istft2_kernel(const __grid_constant__ KbIstftParams p) {
+    extern __shared__ __align__(128) char kb_smem[];
+    kb_istft2_cta<Q>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+template <int Q>
+static int kb_launch_istft2(const KbIstftParams& p, int grid, int smem, cudaStream_t st) {
+    int rc = kb_set_smem(kb_istft2_kernel<Q>, smem);
+    if (rc) return rc;
+    KbProfScope prof(st);
+    kb_istft2_kernel<Q><<<grid, p.n_warps * 32, smem, st>>>(p);
+    KB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+template <int Q>
 static int kb_launch_istft(const KbIstftParams& p, int grid, int smem, cudaStream_t st) {
     int rc = kb_set_smem(kb_istft_kernel<Q>, smem);
     if (rc) return rc;
@@ -879,7 +896,15 @@ int kapre_stft_supports_mode(const kapre_stft_plan* p, int mode) {
     if (!p) return 0;
     if (mode < KAPRE_OUT_COMPLEX || mode > KAPRE_OUT_MAG_PHASE) return 0;
     if (p->Q) return 1;
-    return mode == KAPRE_OUT_COMPLEX || mode == KAPRE_OUT_MAG;
+    if (mode == KAPRE_OUT_COMPLEX || mode == KAPRE_OUT_MAG) return 1;
+    if (mode == KAPRE_OUT_MAG_PHASE) return 0;
+    // fused filterbank / decibel tail of the mixed-radix kernel: 5-smooth transform length whose buffers fit
+    int radix[KB_MR_MAX_PASS];
+    const int P = (p->n_fft & 1) ? p->n_fft : p->n_fft / 2;
+    if (kb_mr_factor(P, radix) < 0 || kb_env_int("KAPRE_B200_NOMR", 0)) return 0;
+    int nw, g, b;
+    // 128 bands as the sizing assumption for the filterbank tile (the launch re-picks with the real count and fails loudly)
+    return kb_mr_pick(P, p->dev.smem_optin, 228 * 1024, 32, &nw, &g, &b, p->n_fft / 2 + 1, 128, 8) > 0 ? 1 : 0;
 }
 
 int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const kapre_wave_desc* xd,
@@ -933,8 +958,8 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     const int pad_left = pad_begin ? (plan->n_fft - plan->hop) : 0;
 
     if (!plan->Q) {
-        if (!(mode == KAPRE_OUT_COMPLEX || mode == KAPRE_OUT_MAG))
-            return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d has no fused filterbank/decibel path; chain the stand-alone ops", plan->n_fft);
+        if (mode == KAPRE_OUT_MAG_PHASE)
+            return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d has no fused magnitude+phase path; chain the stand-alone ops", plan->n_fft);
         KbDftParams p{};
         p.x = x_dev; p.x_sb = xd->stride_b; p.x_sc = xd->stride_c; p.x_sl = xd->stride_l;
         p.B = B; p.C = C; p.L = Ln; p.n_fft = plan->n_fft; p.hop = plan->hop; p.T = T; p.pad_left = pad_left;
@@ -946,29 +971,53 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
             q.half = (plan->n_fft & 1) ? 0 : 1;
             q.P = q.half ? plan->n_fft / 2 : plan->n_fft;
             q.n_pass = kb_mr_factor(q.P, q.radix);
-            int NW = 8;
-            while (NW >= 1 && kb_mr_smem_layout(q.P, NW).total > plan->dev.smem_optin) NW >>= 1;
-            if (q.n_pass >= 0 && NW >= 1 && kb_env_int("KAPRE_B200_NOMR", 0) == 0) {
-                const int smem = kb_mr_smem_layout(q.P, NW).total;
-                int bps = (228 * 1024) / (smem + 1024);
-                if (bps > 16 / NW) bps = 16 / NW;
-                if (bps < 1) bps = 1;
+            int NW = 8, G = 1, bps = 1, FRT = 0, fit = 0;
+            const int want = kb_env_int("KAPRE_B200_MR_WARPS", 32);
+            const int F = plan->n_fft / 2 + 1, nb = fbmode ? fb->n_bands : 0;
+            if (q.n_pass >= 0 && kb_env_int("KAPRE_B200_NOMR", 0) == 0) {
+                if (!fbmode) fit = kb_mr_pick(q.P, plan->dev.smem_optin, 228 * 1024, want, &NW, &G, &bps);
+                else {
+                    // filterbank tile of 32 frames unless a smaller one keeps clearly more warps resident
+                    for (int frt = 32; frt >= 8; frt >>= 1) {
+                        int nw = 8, g = 1, b2 = 1;
+                        const int f2 = kb_mr_pick(q.P, plan->dev.smem_optin, 228 * 1024, want, &nw, &g, &b2, F, nb, frt);
+                        if (f2 > fit + fit / 2) { fit = f2; NW = nw; G = g; bps = b2; FRT = frt; }
+                    }
+                }
+            }
+            if (fit > 0) {
+                const int smem = kb_mr_smem_layout(q.P, NW / G, F, nb, FRT).total;
                 q.d = p; q.d.n_warps = NW;
-                q.TF = 4 * NW;
+                q.G = G;
+                q.pad1 = (q.n_pass > 0 && q.radix[0] % 2 == 0) ? 1 : 0;
+                q.FRT = FRT;
+                q.TF = FRT > 0 ? FRT : 4 * (NW / G);
+                if (fbmode) { q.bands = fb->bands; q.fbw = fb->w; q.n_bands = fb->n_bands; }
+                if (dbmode) {
+                    q.amin = db->amin; q.db_mul = db_mul; q.db_sub = db_sub; q.item_max = (unsigned int*)workspace_dev;
+                    q.db_ftz = (db->amin >= 1.17549435e-38f) ? 1 : 0;
+                }
                 if ((rc = kb_set_smem(kb_mr_kernel, smem))) return rc;
                 const long long tiles = (long long)B * C * ((T + q.TF - 1) / q.TF);
                 const long long gmax = (long long)plan->dev.sm_count * bps;
                 const int grid = (int)(tiles < gmax ? tiles : gmax);
-                KbProfScope prof(st);
-                kb_mr_kernel<<<grid, NW * 32, smem, st>>>(q);
-                KB_CUDA(cudaGetLastError());
-                g_launches++;
+                {
+                    KbProfScope prof(st);
+                    kb_mr_kernel<<<grid, NW * 32, smem, st>>>(q);
+                    KB_CUDA(cudaGetLastError());
+                    g_launches++;
+                }
                 char buf[160];
-                snprintf(buf, sizeof(buf), "MR P%d passes%d NW%d grid%d smem%d bps%d", q.P, q.n_pass, NW, grid, smem, bps);
+                snprintf(buf, sizeof(buf), "MR P%d passes%d NW%d G%d grid%d smem%d bps%d frt%d", q.P, q.n_pass, NW, G, grid, smem, bps, FRT);
                 g_launch_info = buf;
-                return 0;
+                if (dbmode)
+                    rc = kb_launch_clamp((float*)out_dev, B, db_item_size, (unsigned int*)workspace_dev, db->amin, db_mul, db_sub,
+                                         db->dynamic_range, st, db_run, db_period);
+                return rc;
             }
         }
+        if (!(mode == KAPRE_OUT_COMPLEX || mode == KAPRE_OUT_MAG))
+            return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d (prime factor above 5) has no fused filterbank/decibel path; chain the stand-alone ops", plan->n_fft);
         const KbDftSmem L = kb_dft_smem_layout(plan->n_fft, plan->win_eff);
         if (L.total > plan->dev.smem_optin) return kb_fail(KAPRE_E_UNSUPPORTED, "n_fft=%d has a prime factor above 5 and is too large for the direct-DFT kernel (%d B of shared memory needed)", plan->n_fft, L.total);
         if ((rc = kb_set_smem(kb_dft_kernel, L.total))) return rc;
@@ -1208,6 +1257,53 @@ int kapre_istft_inverse(const kapre_istft_plan* plan, const void* stft_dev, int 
 
     const int Q = plan->Q, FPW = 32 / Q;
     const int R = (plan->win + plan->hop - 1) / plan->hop;
+    if (kb_env_int("KAPRE_B200_ISTFT2", 1)) {
+        // streaming kernel: tiles of seg = m * FR - (R - 1) output hops, m rounds of FR = NW * FPW frames each.  m is the
+        // round count that minimises (waves of tiles over the resident CTAs) x (rounds per tile).
+        const int NW = KB_ISTFT_MAX_WARPS, FR = NW * FPW;
+        const KbIstft2Smem L2 = kb_istft2_smem_layout(Q, plan->n_fft, plan->hop, plan->win, NW);
+        if (L2.total <= plan->dev.smem_optin) {
+            int bps = (228 * 1024) / (L2.total + 1024);
+            if (bps > 4) bps = 4;              // __launch_bounds__(128, 4)
+            if (bps < 1) bps = 1;
+            const long long slots = (long long)plan->dev.sm_count * bps;
+            const long long hops = (out_len + plan->hop - 1) / plan->hop;
+            int best_m = 0; long long best_cost = 0; int best_seg = 0;
+            const int m_env = kb_env_int("KAPRE_B200_ISTFT2_M", 0);
+            for (int m = 1; m <= 4096; ++m) {
+                const int seg = m * FR - (R - 1);
+                if (seg < 1) continue;
+                if (m_env > 0 && m != m_env && best_m) continue;
+                const long long nt = (long long)batch * channels * ((hops + seg - 1) / seg);
+                const long long cost = ((nt + slots - 1) / slots) * (2 * m + 1);   // + half a round of per-tile overhead
+                if (!best_m || cost < best_cost || m == m_env) { best_m = m; best_cost = cost; best_seg = seg; }
+                if (m == m_env) break;
+                if (seg >= hops) break;
+            }
+            KbIstftParams p{};
+            p.X = (const float2*)stft_dev; p.x_sb = sd->stride_b; p.x_sc = sd->stride_c; p.x_st = sd->stride_t; p.x_sk = sd->stride_f;
+            p.B = batch; p.C = channels; p.T = frames; p.n_fft = plan->n_fft; p.hop = plan->hop; p.win = plan->win;
+            p.out_len = (int)out_len; p.dual = plan->dual; p.twp = plan->twp; p.twn = plan->twn;
+            p.y = y_dev; p.y_sb = yd->stride_b; p.y_sc = yd->stride_c; p.y_sl = yd->stride_l;
+            p.R = R; p.seg = best_seg; p.n_warps = NW;
+            p.n_tiles_t = kb_istft2_tiles(frames, plan->hop, plan->win_length, best_seg);
+            const long long tiles = (long long)batch * channels * p.n_tiles_t;
+            if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
+            const int grid = (int)(tiles < slots ? tiles : slots);
+            {
+                char buf[160];
+                snprintf(buf, sizeof(buf), "ISTFT2 Q%d NW%d seg%d rounds%d tiles%lld grid%d smem%d bps%d", Q, NW, best_seg, best_m, tiles, grid, L2.total, bps);
+                g_launch_info = buf;
+            }
+            switch (Q) {
+                case 4: return kb_launch_istft2<4>(p, grid, L2.total, st);
+                case 8: return kb_launch_istft2<8>(p, grid, L2.total, st);
+                case 16: return kb_launch_istft2<16>(p, grid, L2.total, st);
+                case 32: return kb_launch_istft2<32>(p, grid, L2.total, st);
+                default: return kb_fail(KAPRE_E_UNSUPPORTED, "bad Q");
+            }
+        }
+    }
     // one FFT round per overlap class: TFc = R * NW * FPW frames per tile
     int NW = kb_env_int("KAPRE_B200_INW", KB_ISTFT_MAX_WARPS), TFc = 0, smem = 0, bps = 0;
     if (NW > KB_ISTFT_MAX_WARPS || NW < 1) NW = KB_ISTFT_MAX_WARPS;

@@ -127,6 +127,7 @@ struct KbIstftParams {
     int hops_out;                        // output hops per tile = TFc - (R - 1)
     int n_tiles_t;
     int n_warps;
+    int seg;                             // streaming kernel (kb_istft2_cta): output hops per tile
 };
 
 // Complex number = one aligned register pair.  On sm_100a the arithmetic below compiles to the

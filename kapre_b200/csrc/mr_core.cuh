@@ -3,13 +3,16 @@
 // ends 400, music 4096 / 8192.  Same semantics as kapre/time_frequency.py:169-182 (pad_begin, right zero-pad of a
 // short window to n_fft, rfft).
 //
-// One warp transforms one frame at a time in shared memory:
+// A group of G warps (G = 1, 2, 4, 8, 16; picked by the host so that ~32 warps are resident per SM whatever the
+// size of the two P-point buffers) transforms one frame at a time in shared memory:
 //   even n_fft: packed real FFT -- complex FFT of length P = n_fft / 2 of z[n] = x[2n] + i x[2n+1], then the pair step
 //               X[k], X[P-k] from Z[k], Z[P-k] (as in stft_core.cuh);   odd n_fft: complex FFT of length P = n_fft.
 //   Stockham autosort passes (ping-pong between two P-point buffers, natural order in and out), pass with radix r
 //   after radices of product Ns:   lane j < P / r:  k = j mod Ns,
 //       v[t] = in[j + t P / r] * exp(-2 pi i t k / (Ns r)),  V = DFT_r(v),  out[(j - k) r + k + t Ns] = V[t]
-//   twiddles from one shared table exp(-2 pi i m / P).
+//   twiddles from one shared table exp(-2 pi i m / P).  The first pass writes with a lane stride of r elements; when r is
+//   even that hand-off buffer is indexed as i + (i >> 4) (one spare element per 16), which spreads the 16 lanes of a
+//   half-warp over all banks; later passes (Ns >= r) are at most 2-way conflicted and stay unpadded.
 // Instruction count per frame is about 1.5x the register kernel's at the neighbouring power of two (4 passes over
 // shared memory instead of 1 transpose), against ~100x for the direct O(N^2) DFT it replaces (kb_dft_cta stays for
 // sizes with a prime factor > 5).
@@ -24,7 +27,17 @@ struct KbMrParams {
     int half;                 // 1: packed real FFT (even n_fft)
     int n_pass;
     int radix[KB_MR_MAX_PASS];
-    int TF;                   // frames per tile (= frames per warp per tile * n_warps)
+    int TF;                   // frames per tile (= frames per group per tile * n_warps / G)
+    int G;                    // warps per frame
+    int pad1;                 // the buffer between pass 0 and pass 1 is indexed i + (i >> 4)
+    // fused tail (modes KB_OUT_MAG_DB, KB_OUT_FB, KB_OUT_FB_DB; kapre/time_frequency.py:535-548, kapre/backend.py:186-192)
+    int FRT;                  // filterbank modes: frames per tile (32 / 16 / 8) = columns of the magnitude tile; else 0
+    const KbBand* bands;
+    const float* fbw;
+    int n_bands;
+    float amin, db_mul, db_sub;
+    int db_ftz;
+    unsigned int* item_max;   // per batch item: bits of max(max(x, amin)) for the clamp pass
 };
 
 // radices of P in {8, 4, 2, 3, 5} order (large radices first: fewest passes over shared memory); returns -1 if P has
@@ -39,13 +52,38 @@ static inline int kb_mr_factor(int P, int* radix) {
     return P == 1 ? n : -1;
 }
 
-struct KbMrSmem { int tw, buf, total; };
-KB_HD KbMrSmem kb_mr_smem_layout(int P, int n_warps) {
+struct KbMrSmem { int tw, buf, mag, outs, total, Mp; };
+KB_HD int kb_mr_bufsz(int P) { return kb_align16((P + (P >> 4) + 1) * 8); }
+// FRT > 0 adds the filterbank tile: magnitudes [bin][frame] (row stride FRT + 1, three zero pad rows for the 4-bin
+// groups of kb_band_dot) and the (frame x band) result block
+KB_HD KbMrSmem kb_mr_smem_layout(int P, int n_groups, int F = 0, int n_bands = 0, int FRT = 0) {
     KbMrSmem s;
     s.tw = 0;
     s.buf = kb_align16(P * 8);
-    s.total = s.buf + n_warps * 2 * kb_align16(P * 8);
+    s.mag = s.buf + n_groups * 2 * kb_mr_bufsz(P);
+    s.Mp = n_bands | 1;
+    s.outs = s.mag + (FRT > 0 ? kb_align16((F + 3) * (FRT + 1) * 4) : 0);
+    s.total = s.outs + (FRT > 0 ? kb_align16(FRT * s.Mp * 4) : 0);
     return s;
+}
+
+// launch shape: the fewest warps per frame (G) that make `want` warps resident per SM (64 registers per thread: 32), given
+// tw + 2 buffers per group; larger G only when nothing smaller reaches the best residency.  Returns warps per SM, 0 if
+// even one group does not fit.
+static inline int kb_mr_pick(int P, int smem_optin, int smem_sm, int want, int* NW_out, int* G_out, int* bps_out,
+                             int F = 0, int n_bands = 0, int FRT = 0) {
+    int best = 0;
+    for (int NW = 8; NW <= 16; NW += 8)
+        for (int G = 1; G <= NW; G *= 2) {
+            if (FRT > 0 && (NW / G > FRT || FRT % (NW / G))) continue;     // whole frames per group and tile
+            const int smem = kb_mr_smem_layout(P, NW / G, F, n_bands, FRT).total;
+            if (smem > smem_optin) continue;
+            int bps = smem_sm / (smem + 1024);
+            if (bps * NW > want) bps = want / NW;
+            if (bps < 1) continue;
+            if (bps * NW > best) { best = bps * NW; *NW_out = NW; *G_out = G; *bps_out = bps; }
+        }
+    return best;
 }
 
 KB_HD cpx kb_mul_mi(cpx a) { return cmake(a.im, -a.re); }   // a * (-i)
@@ -87,17 +125,17 @@ KB_HD void kb_dft_r5(cpx* v) {
     v[2] = cadd(r2, q2); v[3] = csub(r2, q2);
 }
 
-// one Stockham pass of radix RDX for the calling lane (all butterflies j = lane, lane + 32, ...)
-template <int RDX>
-KB_FN void kb_mr_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw_s, int P, int Ns, int lane) {
+// one Stockham pass of radix RDX for thread gl of a group of GS threads (butterflies j = gl, gl + GS, ...)
+template <int RDX, bool PIN, bool POUT>
+KB_FN void kb_mr_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw_s, int P, int Ns, int gl, int GS) {
     const int nb = P / RDX;                 // butterflies
     const int tstep = P / (Ns * RDX);       // exp(-2 pi i t k / (Ns r)) = tw_s[t k tstep]
-    int k = lane % Ns;                      // j mod Ns, stepped with j (one division per pass, not per butterfly)
-    const int kinc = 32 % Ns;
-    for (int j = lane; j < nb; j += 32, k = (k + kinc >= Ns) ? k + kinc - Ns : k + kinc) {
+    int k = gl % Ns;                        // j mod Ns, stepped with j (two divisions per pass, not per butterfly)
+    const int kinc = GS % Ns;
+    for (int j = gl; j < nb; j += GS, k = (k + kinc >= Ns) ? k + kinc - Ns : k + kinc) {
         cpx v[RDX];
 #pragma unroll
-        for (int t = 0; t < RDX; ++t) v[t] = in[j + t * nb];
+        for (int t = 0; t < RDX; ++t) { const int i = j + t * nb; v[t] = in[PIN ? i + (i >> 4) : i]; }
         if (Ns > 1) {
             const int kt = k * tstep;
             int ti = kt;
@@ -111,27 +149,49 @@ KB_FN void kb_mr_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const c
         else kb_dft_r5(v);
         const int j0 = (j - k) * RDX + k;
 #pragma unroll
-        for (int t = 0; t < RDX; ++t) out[j0 + t * Ns] = v[t];
+        for (int t = 0; t < RDX; ++t) { const int i = j0 + t * Ns; out[POUT ? i + (i >> 4) : i] = v[t]; }
     }
 }
+template <bool PIN, bool POUT>
+KB_FN void kb_mr_pass_r(int r, const cpx* in, cpx* out, const cpx* tw_s, int P, int Ns, int gl, int GS) {
+    if (r == 8) kb_mr_pass<8, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
+    else if (r == 4) kb_mr_pass<4, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
+    else if (r == 2) kb_mr_pass<2, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
+    else if (r == 3) kb_mr_pass<3, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
+    else kb_mr_pass<5, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
+}
 
+// synchronisation of one frame group: a warp barrier when G == 1, else a named barrier (ids 1 .. 15) over its G warps
 #if defined(KB_HOST_EMU)
-inline void kb_mr_cta(const KbMrParams& q, char* smem, int cta, int n_cta)
+#define KB_MR_SYNC
 #else
-__device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int cta, int n_cta)
+#define KB_MR_SYNC do { if (q.G == 1) __syncwarp(); else asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)(threadIdx.x >> 5) / q.G), "r"(q.G * 32) : "memory"); } while (0)
+#endif
+
+template <int FRT>
+#if defined(KB_HOST_EMU)
+inline void kb_mr_cta_t(const KbMrParams& q, char* smem, int cta, int n_cta)
+#else
+__device__ __forceinline__ void kb_mr_cta_t(const KbMrParams& q, char* smem, int cta, int n_cta)
 #endif
 {
+    constexpr int RS = FRT + 1;
     const KbDftParams& p = q.d;
     const int NW = p.n_warps;
     const int kb_nt = NW * 32;
     (void)kb_nt;
     const int N = p.n_fft, We = p.win_eff, F = N / 2 + 1, P = q.P;
-    const KbMrSmem L = kb_mr_smem_layout(P, NW);
+    const int G = q.G, GS = G * 32, NG = NW / G;
+    const KbMrSmem L = kb_mr_smem_layout(P, NG, F, q.n_bands, FRT);
     cpx* tw_s = reinterpret_cast<cpx*>(smem + L.tw);
-    const int bufsz = kb_align16(P * 8);
+    float* mag_s = reinterpret_cast<float*>(smem + L.mag);
+    float* out_s = reinterpret_cast<float*>(smem + L.outs);
+    const bool dbmode = p.mode == KB_OUT_MAG_DB || p.mode == KB_OUT_FB_DB;
+    (void)mag_s; (void)out_s;
+    const int bufsz = kb_mr_bufsz(P);
     const int n_tiles_t = (p.T + q.TF - 1) / q.TF;
     const int n_tiles = p.B * p.C * n_tiles_t;
-    const int fpw = q.TF / NW;               // frames per warp and tile
+    const int fpw = q.TF / NG;               // frames per group and tile
 #if defined(KB_HOST_EMU)
     std::vector<KbThreadRegs> kb_regs(kb_nt);
 #else
@@ -141,6 +201,7 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
         (void)R;
         const int st = q.half ? 2 : 1;
         for (int i = tid; i < P; i += kb_nt) { float2 t = p.tw[i * st]; tw_s[i] = cmake(t.x, t.y); }
+        if (FRT > 0) for (int i = tid; i < 3 * RS; i += kb_nt) mag_s[F * RS + i] = 0.0f;   // pad rows, never written again
     KB_PHASE_END
     KB_SYNC_CTA;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
@@ -149,13 +210,16 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
         const int b = sig / p.C, c = sig - b * p.C;
         const float* xsig = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc;
         const long long obase = (long long)b * p.o_sb + (long long)c * p.o_sc;
+        KB_PHASE_BEGIN
+            R.runmax = 0.0f;
+        KB_PHASE_END
         for (int fi = 0; fi < fpw; ++fi) {
-            // every step below is private to one warp (its own two buffers): warp-level synchronisation only
+            // every step below is private to one group of G warps (its own two buffers): group-level synchronisation only
             KB_PHASE_BEGIN
                 (void)R;
-                const int warp = tid >> 5, lane = tid & 31;
-                const int t = tt * q.TF + warp * fpw + fi;
-                cpx* A = reinterpret_cast<cpx*>(smem + L.buf + (warp * 2) * bufsz);
+                const int grp = tid / GS, gl = tid - grp * GS;
+                const int t = tt * q.TF + grp * fpw + fi;
+                cpx* A = reinterpret_cast<cpx*>(smem + L.buf + (grp * 2) * bufsz);
                 if (t < p.T) {
                     const long long s0 = (long long)t * p.hop - p.pad_left;
                     const bool interior = s0 >= 0 && s0 + N <= p.L && We == N && p.x_sl == 1 &&
@@ -164,7 +228,7 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
                         // whole frame inside the signal, 8-byte aligned: one vector load of (x[2n], x[2n+1]) and of the window pair
                         const float2* xp = reinterpret_cast<const float2*>(xsig + s0);
                         const float2* wp = reinterpret_cast<const float2*>(p.w);
-                        for (int n = lane; n < P; n += 32) {
+                        for (int n = gl; n < P; n += GS) {
 #if defined(KB_HOST_EMU)
                             const float2 xv = xp[n], wv = wp[n];
 #else
@@ -173,7 +237,7 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
                             A[n] = cmake(xv.x * wv.x, xv.y * wv.y);
                         }
                     } else if (q.half) {
-                        for (int n = lane; n < P; n += 32) {
+                        for (int n = gl; n < P; n += GS) {
                             float v[2];
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
@@ -184,7 +248,7 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
                             A[n] = cmake(v[0], v[1]);
                         }
                     } else {
-                        for (int n = lane; n < P; n += 32) {
+                        for (int n = gl; n < P; n += GS) {
                             const long long s = s0 + n;
                             const float v = (n < We && s >= 0 && s < p.L) ? kb_ldg(xsig + s * p.x_sl) * kb_ldg(p.w + n) : 0.0f;
                             A[n] = cmake(v, 0.0f);
@@ -192,62 +256,134 @@ __device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int c
                     }
                 }
             KB_PHASE_END
-            KB_SYNC_WARP;
+            KB_MR_SYNC;
             int Ns = 1;
             for (int ps = 0; ps < q.n_pass; ++ps) {
                 const int r = q.radix[ps];
                 KB_PHASE_BEGIN
                     (void)R;
-                    const int warp = tid >> 5, lane = tid & 31;
-                    const int t = tt * q.TF + warp * fpw + fi;
-                    cpx* b0 = reinterpret_cast<cpx*>(smem + L.buf + (warp * 2) * bufsz);
-                    cpx* b1 = reinterpret_cast<cpx*>(smem + L.buf + (warp * 2 + 1) * bufsz);
+                    const int grp = tid / GS, gl = tid - grp * GS;
+                    const int t = tt * q.TF + grp * fpw + fi;
+                    cpx* b0 = reinterpret_cast<cpx*>(smem + L.buf + (grp * 2) * bufsz);
+                    cpx* b1 = reinterpret_cast<cpx*>(smem + L.buf + (grp * 2 + 1) * bufsz);
                     const cpx* in = (ps & 1) ? b1 : b0;
                     cpx* out = (ps & 1) ? b0 : b1;
                     if (t < p.T) {
-                        if (r == 8) kb_mr_pass<8>(in, out, tw_s, P, Ns, lane);
-                        else if (r == 4) kb_mr_pass<4>(in, out, tw_s, P, Ns, lane);
-                        else if (r == 2) kb_mr_pass<2>(in, out, tw_s, P, Ns, lane);
-                        else if (r == 3) kb_mr_pass<3>(in, out, tw_s, P, Ns, lane);
-                        else kb_mr_pass<5>(in, out, tw_s, P, Ns, lane);
+                        if (q.pad1 && ps == 0) kb_mr_pass_r<false, true>(r, in, out, tw_s, P, Ns, gl, GS);
+                        else if (q.pad1 && ps == 1) kb_mr_pass_r<true, false>(r, in, out, tw_s, P, Ns, gl, GS);
+                        else kb_mr_pass_r<false, false>(r, in, out, tw_s, P, Ns, gl, GS);
                     }
                 KB_PHASE_END
-                KB_SYNC_WARP;
+                KB_MR_SYNC;
                 Ns *= r;
             }
             KB_PHASE_BEGIN
-                (void)R;
-                const int warp = tid >> 5, lane = tid & 31;
-                const int t = tt * q.TF + warp * fpw + fi;
-                const cpx* Z = reinterpret_cast<const cpx*>(smem + L.buf + (warp * 2 + (q.n_pass & 1)) * bufsz);
+                const int grp = tid / GS, gl = tid - grp * GS;
+                const int t = tt * q.TF + grp * fpw + fi;
+                const cpx* Z = reinterpret_cast<const cpx*>(smem + L.buf + (grp * 2 + (q.n_pass & 1)) * bufsz);
+                const bool zp = q.pad1 && q.n_pass == 1;   // a single pass leaves its (padded) output as the spectrum
                 if (t < p.T) {
                     const long long o = obase + (long long)t * p.o_st;
                     float2* oc = reinterpret_cast<float2*>(p.out) + o;
                     float* orl = reinterpret_cast<float*>(p.out) + o;
-                    if (q.half) {
-                        // X[k] = (Z[k] + conj Z[P-k]) / 2 - i/2 exp(-2 pi i k / N) (Z[k] - conj Z[P-k]),  k = 0 .. P
-                        for (int k = lane; k <= P; k += 32) {
-                            const cpx a = Z[k == P ? 0 : k];
-                            const cpx bq = Z[k == 0 || k == P ? 0 : P - k];
+                    float* mcol = mag_s + (grp * fpw + fi);          // FRT > 0: this frame's column of the magnitude tile
+                    (void)mcol;
+                    float rmax = R.runmax;
+                    const int kend = q.half ? P + 1 : F;
+                    for (int k = gl; k < kend; k += GS) {
+                        cpx X;
+                        if (q.half) {
+                            // X[k] = (Z[k] + conj Z[P-k]) / 2 - i/2 exp(-2 pi i k / N) (Z[k] - conj Z[P-k]),  k = 0 .. P
+                            const int ia = k == P ? 0 : k, ib = (k == 0 || k == P) ? 0 : P - k;
+                            const cpx a = Z[zp ? ia + (ia >> 4) : ia];
+                            const cpx bq = Z[zp ? ib + (ib >> 4) : ib];
                             const cpx e = cadd_conj(a, bq), dd = csub_conj(a, bq);
                             float2 w2;
                             if (k == P) w2 = make_float2(-1.0f, 0.0f);
                             else { w2.x = kb_ldg(reinterpret_cast<const float*>(p.tw + k)); w2.y = kb_ldg(reinterpret_cast<const float*>(p.tw + k) + 1); }
                             const cpx tq = cmul(cmake(dd.im, -dd.re), cmake(w2.x, w2.y));
-                            const cpx X = cscale(cadd(e, tq), 0.5f);
-                            if (p.mode == KB_OUT_COMPLEX) oc[(long long)k * p.o_sk] = make_float2(X.re, X.im);
-                            else orl[(long long)k * p.o_sk] = kb_sqrt(cnorm(X));
+                            X = cscale(cadd(e, tq), 0.5f);
+                        } else {
+                            X = Z[zp ? k + (k >> 4) : k];
                         }
-                    } else {
-                        for (int k = lane; k < F; k += 32) {
-                            const cpx X = Z[k];
-                            if (p.mode == KB_OUT_COMPLEX) oc[(long long)k * p.o_sk] = make_float2(X.re, X.im);
-                            else orl[(long long)k * p.o_sk] = kb_sqrt(cnorm(X));
+                        if (p.mode == KB_OUT_COMPLEX) { oc[(long long)k * p.o_sk] = make_float2(X.re, X.im); continue; }
+                        float v = kb_sqrt(cnorm(X));
+                        if (FRT > 0) { mcol[k * RS] = v; continue; }
+                        if (p.mode == KB_OUT_MAG_DB) {
+                            v = kb_floor_keepnan(v, q.amin);
+                            rmax = kb_max_keepnan(rmax, v);
+                            v = q.db_mul * (q.db_ftz ? kb_lg2_ftz(v) : kb_log2(v)) - q.db_sub;
                         }
+                        orl[(long long)k * p.o_sk] = v;
+                    }
+                    R.runmax = rmax;
+                }
+            KB_PHASE_END
+            KB_MR_SYNC;
+        }
+        if (FRT > 0) {
+            // ---- filterbank over the tile: lane = frame column, warps stride over the bands (as kb_fb_cta_r) ----
+            KB_SYNC_CTA;
+            KB_PHASE_BEGIN
+                (void)R;
+                const int warp = tid >> 5, lane = tid & 31;
+                if (lane < FRT) {
+                    const float* mcol = mag_s + lane;
+                    for (int m = warp; m < q.n_bands; m += NW) {
+                        const KbBand bd = q.bands[m];
+                        out_s[lane * L.Mp + m] = kb_band_dot<RS>(q.fbw + bd.off, mcol + bd.lo * RS, (bd.hi - bd.lo) >> 2);
                     }
                 }
             KB_PHASE_END
-            KB_SYNC_WARP;
+            KB_SYNC_CTA;
+            // ---- decibel + coalesced copy-out of the (FRT x n_bands) block ----
+            KB_PHASE_BEGIN
+                const int warp = tid >> 5, lane = tid & 31;
+                float* o = reinterpret_cast<float*>(p.out) + obase;
+                const int M = q.n_bands;
+                float rmax = R.runmax;
+                for (int r = warp; r < FRT; r += NW) {
+                    const int t = tt * q.TF + r;
+                    if (t >= p.T) continue;
+                    const float* srow = out_s + r * L.Mp;
+                    float* orow = o + (long long)t * p.o_st;
+                    for (int m = lane; m < M; m += 32) {
+                        float v = srow[m];
+                        if (dbmode) {
+                            v = kb_floor_keepnan(v, q.amin);
+                            rmax = kb_max_keepnan(rmax, v);
+                            v = q.db_mul * (q.db_ftz ? kb_lg2_ftz(v) : kb_log2(v)) - q.db_sub;
+                        }
+                        orow[(long long)m * p.o_sk] = v;
+                    }
+                }
+                R.runmax = rmax;
+            KB_PHASE_END
+            KB_SYNC_CTA;      // the next tile's frames overwrite the magnitude tile
         }
+        // ---- per-item maximum for the decibel clamp (kapre/backend.py:190-192) ----
+        if (dbmode) {
+#if defined(KB_HOST_EMU)
+            for (int tid = 0; tid < kb_nt; ++tid)
+                kb_atomic_max_u32(q.item_max + b, kb_f2u(kb_regs[tid].runmax));
+#else
+            const unsigned int wm = __reduce_max_sync(0xffffffffu, kb_f2u(kb_regs.runmax));
+            if ((threadIdx.x & 31) == 0 && wm != 0u) kb_atomic_max_u32(q.item_max + b, wm);
+#endif
+        }
+    }
+}
+
+#if defined(KB_HOST_EMU)
+inline void kb_mr_cta(const KbMrParams& q, char* smem, int cta, int n_cta)
+#else
+__device__ __forceinline__ void kb_mr_cta(const KbMrParams& q, char* smem, int cta, int n_cta)
+#endif
+{
+    switch (q.FRT) {
+        case 32: kb_mr_cta_t<32>(q, smem, cta, n_cta); break;
+        case 16: kb_mr_cta_t<16>(q, smem, cta, n_cta); break;
+        case 8: kb_mr_cta_t<8>(q, smem, cta, n_cta); break;
+        default: kb_mr_cta_t<0>(q, smem, cta, n_cta); break;
     }
 }

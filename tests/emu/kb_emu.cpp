@@ -87,6 +87,16 @@ static void run_istft(const KbIstftParams& p, int n_cta) {
     }
 }
 
+template <int Q>
+static void run_istft2(const KbIstftParams& p, int n_cta) {
+    const KbIstft2Smem L = kb_istft2_smem_layout(Q, p.n_fft, p.hop, p.win, p.n_warps);
+    std::vector<char> smem(L.total + 64);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        std::fill(smem.begin(), smem.end(), (char)0x7f);
+        kb_istft2_cta<Q>(p, smem.data(), cta, n_cta);
+    }
+}
+
 extern "C" {
 
 int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, int B, int C, int L,
@@ -231,6 +241,36 @@ int kb_emu_istft(const float* X, long long x_sb, long long x_sc, long long x_st,
 }
 
 
+int kb_emu_istft2(const float* X, long long x_sb, long long x_sc, long long x_st, long long x_sk,
+                  int B, int C, int T, int n_fft, int win_length, int hop, const float* dual_window,
+                  float* y, long long y_sb, long long y_sc, long long y_sl, int seg, int n_warps, int n_cta) {
+    const int Q = kb_q_for_nfft(n_fft);
+    if (!Q) return -1;
+    std::vector<float> dual;
+    std::vector<float2> twp, twn;
+    const int win = win_length < n_fft ? win_length : n_fft;
+    kb_make_dual(dual_window, win, n_fft, dual);
+    kb_make_twp(Q, twp);
+    kb_make_twn(n_fft, twn);
+    KbIstftParams p{};
+    p.X = reinterpret_cast<const float2*>(X); p.x_sb = x_sb; p.x_sc = x_sc; p.x_st = x_st; p.x_sk = x_sk;
+    p.B = B; p.C = C; p.T = T; p.n_fft = n_fft; p.hop = hop; p.win = win;
+    p.out_len = (T - 1) * hop + win_length;
+    p.dual = dual.data(); p.twp = twp.data(); p.twn = twn.data();
+    p.y = y; p.y_sb = y_sb; p.y_sc = y_sc; p.y_sl = y_sl;
+    p.R = (win + hop - 1) / hop; p.seg = seg;
+    p.n_tiles_t = kb_istft2_tiles(T, hop, win_length, seg);
+    p.n_warps = n_warps;
+    switch (Q) {
+        case 4: run_istft2<4>(p, n_cta); break;
+        case 8: run_istft2<8>(p, n_cta); break;
+        case 16: run_istft2<16>(p, n_cta); break;
+        case 32: run_istft2<32>(p, n_cta); break;
+    }
+    return 0;
+}
+
+
 // ---- stand-alone / generic-n_fft kernel bodies (aux_core.cuh) -----------------------------------
 int kb_emu_dft(const float* x, long long x_sb, long long x_sc, long long x_sl, int B, int C, int L,
                int n_fft, int win_length, int hop, int pad_left, int T, const float* window, int mode,
@@ -258,7 +298,8 @@ int kb_emu_dft(const float* x, long long x_sb, long long x_sc, long long x_sl, i
 // Mixed-radix Stockham kernel (mr_core.cuh).  Returns -3 when n_fft has a prime factor > 5.
 int kb_emu_mr(const float* x, long long x_sb, long long x_sc, long long x_sl, int B, int C, int L,
               int n_fft, int win_length, int hop, int pad_left, int T, const float* window, int mode,
-              void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk, int n_warps, int fpw, int n_cta) {
+              void* out, long long o_sb, long long o_sc, long long o_st, long long o_sk, int n_warps, int fpw, int n_cta, int group,
+              const float* fb, int n_freq, int n_bands, float amin, float db_mul, float db_sub, unsigned int* item_max, int frt) {
     const int win_eff = win_length < n_fft ? win_length : n_fft;
     std::vector<float2> tw(n_fft);
     for (int r = 0; r < n_fft; ++r) {
@@ -274,8 +315,20 @@ int kb_emu_mr(const float* x, long long x_sb, long long x_sc, long long x_sl, in
     q.P = q.half ? n_fft / 2 : n_fft;
     q.n_pass = kb_mr_factor(q.P, q.radix);
     if (q.n_pass < 0) return -3;
-    q.TF = fpw * n_warps;
-    const KbMrSmem L_ = kb_mr_smem_layout(q.P, n_warps);
+    if (group < 1 || n_warps % group) return -4;
+    q.G = group;
+    q.pad1 = (q.n_pass > 0 && q.radix[0] % 2 == 0) ? 1 : 0;
+    q.TF = fpw * (n_warps / group);
+    std::vector<KbBand> bands; std::vector<float> fbw;
+    const bool fbm = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
+    if (fbm) {
+        if (!fb || n_freq != n_fft / 2 + 1 || frt < 1 || frt % (n_warps / group) || n_warps / group > frt) return -5;
+        kb_make_bands(fb, n_freq, n_bands, bands, fbw);
+        q.FRT = frt; q.TF = frt; q.bands = bands.data(); q.fbw = fbw.data(); q.n_bands = n_bands;
+    }
+    q.amin = amin; q.db_mul = db_mul; q.db_sub = db_sub; q.item_max = item_max;
+    q.db_ftz = (amin >= 1.17549435e-38f) ? 1 : 0;
+    const KbMrSmem L_ = kb_mr_smem_layout(q.P, n_warps / group, n_fft / 2 + 1, q.n_bands, q.FRT);
     std::vector<char> smem(L_.total + 64);
     for (int cta = 0; cta < n_cta; ++cta) {
         std::fill(smem.begin(), smem.end(), (char)0x7f);

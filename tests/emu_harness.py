@@ -120,8 +120,9 @@ def emu_stft_mc(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_
     return out, item_max.view(np.float32)
 
 
-def emu_istft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, TFc=16, n_warps=4, n_cta=3):
-    """X: (B, T, F, C) channels_last or (B, C, T, F) channels_first complex64."""
+def emu_istft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, TFc=16, n_warps=4, n_cta=3, seg=None):
+    """X: (B, T, F, C) channels_last or (B, C, T, F) channels_first complex64.  seg=None: the class-ordered overlap-add
+    body (kb_istft_cta, tiles of TFc frames); seg=k: the streaming body (kb_istft2_cta, tiles of k output hops)."""
     lib = load()
     X = np.ascontiguousarray(X, dtype=np.complex64)
     if in_fmt == 'channels_last':
@@ -139,8 +140,12 @@ def emu_istft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, TFc=16, n
         ysb, ysc, ysl = C * out_len, out_len, 1
     dual = np.ascontiguousarray(dual_window, dtype=np.float32)
     LL = ctypes.c_longlong
-    rc = lib.kb_emu_istft(_fp(X), LL(sb), LL(sc), LL(st), LL(sk), B, C, T, n_fft, win_length, hop,
-                          _fp(dual), _fp(y), LL(ysb), LL(ysc), LL(ysl), TFc, n_warps, n_cta)
+    if seg is not None:
+        rc = lib.kb_emu_istft2(_fp(X), LL(sb), LL(sc), LL(st), LL(sk), B, C, T, n_fft, win_length, hop,
+                               _fp(dual), _fp(y), LL(ysb), LL(ysc), LL(ysl), int(seg), n_warps, n_cta)
+    else:
+        rc = lib.kb_emu_istft(_fp(X), LL(sb), LL(sc), LL(st), LL(sk), B, C, T, n_fft, win_length, hop,
+                              _fp(dual), _fp(y), LL(ysb), LL(ysc), LL(ysl), TFc, n_warps, n_cta)
     assert rc == 0
     return y
 
@@ -176,9 +181,11 @@ def emu_dft(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt,
     return out
 
 
-def emu_mr(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, out_fmt, n_warps=4, fpw=2, n_cta=3):
-    """Mixed-radix Stockham forward kernel body (mr_core.cuh kb_mr_cta): complex or magnitude output.
-    Returns None when n_fft has a prime factor above 5 (the library then uses the direct DFT)."""
+def emu_mr(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, out_fmt, n_warps=4, fpw=2, n_cta=3, group=1,
+           fb=None, amin=1e-5, ref=1.0, frt=8, with_item_max=False):
+    """Mixed-radix Stockham forward kernel body (mr_core.cuh kb_mr_cta): complex or magnitude output, or the fused
+    tail (MODE_MAG_DB, MODE_FB, MODE_FB_DB; filterbank tiles of `frt` frames).  Returns None when n_fft has a prime
+    factor above 5 (the library then uses the direct DFT); (out, item_max) with with_item_max."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float32)
     if in_fmt == 'channels_last':
@@ -190,16 +197,26 @@ def emu_mr(x, n_fft, win_length, hop, window, pad_begin, pad_end, mode, in_fmt, 
     pad_left = (n_fft - hop) if pad_begin else 0
     Lp = L + pad_left
     T = -(-Lp // hop) if pad_end else max(0, 1 + (Lp - win_length) // hop)
-    shape, (osb, osc, ost, osk) = _strides4((B, C, T, n_fft // 2 + 1), out_fmt)
+    K = fb.shape[1] if mode in (MODE_FB, MODE_FB_DB) else n_fft // 2 + 1
+    shape, (osb, osc, ost, osk) = _strides4((B, C, T, K), out_fmt)
     out = np.full(shape, np.nan, dtype=np.complex64 if mode == MODE_COMPLEX else np.float32)
     window = np.ascontiguousarray(window, dtype=np.float32)
+    item_max = np.zeros(B, dtype=np.uint32)
+    fbp, nfreq, nb = None, 0, 0
+    if fb is not None:
+        fb = np.ascontiguousarray(fb, dtype=np.float32)
+        fbp, nfreq, nb = _fp(fb), fb.shape[0], fb.shape[1]
+    db_mul = 10.0 * np.log10(2.0)
+    db_sub = 10.0 * np.log10(max(amin, ref))
     LL = ctypes.c_longlong
     rc = lib.kb_emu_mr(_fp(x), LL(sb), LL(sc), LL(sl), B, C, L, n_fft, win_length, hop, pad_left, T, _fp(window),
-                       mode, _fp(out), LL(osb), LL(osc), LL(ost), LL(osk), n_warps, fpw, n_cta)
+                       mode, _fp(out), LL(osb), LL(osc), LL(ost), LL(osk), n_warps, fpw, n_cta, group,
+                       fbp, nfreq, nb, ctypes.c_float(amin), ctypes.c_float(db_mul), ctypes.c_float(db_sub),
+                       _fp(item_max), int(frt))
     if rc == -3:
         return None
-    assert rc == 0
-    return out
+    assert rc == 0, rc
+    return (out, item_max.view(np.float32)) if with_item_max else out
 
 
 def emu_idft(X, n_fft, win_length, hop, dual_window, in_fmt, out_fmt, n_cta=3):

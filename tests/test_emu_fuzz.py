@@ -91,6 +91,9 @@ def test_fuzz_inverse(n_fft, hop_div, frames, C, ifmt, ofmt, nw, seed):
     y = E.emu_istft(X, n_fft, n_fft, hop, dual, ifmt, ofmt, TFc=R * nw * fpw, n_warps=nw, n_cta=1 + seed % 3)
     assert y.shape == ref.shape
     assert _nerr(y, ref) < 3e-6
+    y2 = E.emu_istft(X, n_fft, n_fft, hop, dual, ifmt, ofmt, seg=1 + seed % 50, n_warps=nw, n_cta=1 + seed % 3)   # streaming body
+    assert not np.isnan(y2).any()
+    assert _nerr(y2, ref) < 3e-6
 
 
 @settings(**COMMON)
@@ -138,8 +141,9 @@ def test_fuzz_generic_n_fft(n_fft, win_frac, hop, L, C, pad_begin, pad_end, fmt,
     out = E.emu_dft(x, n_fft, win, hop, w, pad_begin, pad_end, E.MODE_COMPLEX, fmt, fmt, n_cta=1 + seed % 3)
     assert out.shape == ref.shape
     assert _nerr(out, ref) < 5e-6
-    mr = E.emu_mr(x, n_fft, win, hop, w, pad_begin, pad_end, E.MODE_COMPLEX, fmt, fmt, n_warps=1 + seed % 4,
-                  fpw=1 + seed % 3, n_cta=1 + seed % 3)           # the Stockham kernel, when n_fft is 5-smooth
+    grp = (1, 2, 4)[seed % 3]
+    mr = E.emu_mr(x, n_fft, win, hop, w, pad_begin, pad_end, E.MODE_COMPLEX, fmt, fmt, n_warps=grp * (1 + seed % 4),
+                  fpw=1 + seed % 3, n_cta=1 + seed % 3, group=grp)   # the Stockham kernel, when n_fft is 5-smooth
     if mr is not None:
         assert mr.shape == ref.shape
         assert _nerr(mr, ref) < 5e-6

@@ -141,6 +141,31 @@ def test_emu_istft(n_fft, hop, win, TFc, nw, ifmt, ofmt):
     assert nerr(y, ref) < 1e-6
 
 
+@pytest.mark.parametrize('n_fft,hop,win,seg,nw', [(1024, 256, 1024, 5, 4), (1024, 256, 1024, 13, 2), (2048, 1024, 2048, 3, 4),
+                                                   (2048, 256, 2048, 9, 4), (512, 128, 400, 29, 2), (256, 100, 256, 7, 2),
+                                                   (256, 300, 256, 4, 1), (512, 37, 512, 100, 1), (1024, 256, 1024, 1, 4),
+                                                   (512, 128, 512, 41, 4), (256, 64, 250, 6, 3)])
+@pytest.mark.parametrize('ifmt', ['channels_first', 'channels_last'])
+@pytest.mark.parametrize('ofmt', ['channels_first', 'channels_last'])
+def test_emu_istft_streaming(n_fft, hop, win, seg, nw, ifmt, ofmt):
+    """istft_core.cuh kb_istft2_cta: frames left in the exchange regions, gather-sum with a carry between rounds; hop > win
+    (gaps), odd hops (scalar gather), a window shorter than n_fft, tiles of one hop and of the whole signal."""
+    rng = np.random.default_rng(n_fft + hop + seg)
+    B, C, T, F = 2, 2, 37, n_fft // 2 + 1
+    shp = (B, C, T, F) if ifmt == 'channels_first' else (B, T, F, C)
+    X = (rng.normal(size=shp) + 1j * rng.normal(size=shp)).astype(np.complex64)
+    if hop <= win:
+        dual = O.inverse_stft_window(win, hop, O.get_window(None, win))
+        ref = O.istft_layer(X, n_fft, win, hop, None, ifmt, ofmt)
+    else:                      # no overlap: any window will do, compare with the class-ordered body
+        dual = O.get_window(None, win)
+        ref = E.emu_istft(X, n_fft, win, hop, dual, ifmt, ofmt, TFc=4, n_warps=1, n_cta=1)
+    y = E.emu_istft(X, n_fft, win, hop, dual, ifmt, ofmt, seg=seg, n_warps=nw, n_cta=2)
+    assert y.shape == ref.shape
+    assert not np.isnan(y).any()
+    assert nerr(y, ref) < 1e-6
+
+
 # ------------------------------------------------------------------------------- multi-channel tiles
 @pytest.mark.parametrize('n_fft,hop,win,C,TF,nw', [(2048, 1024, 2048, 6, 1, 6), (2048, 1024, 2048, 6, 2, 4),
                                                   (1024, 256, 1024, 2, 8, 8), (512, 128, 400, 3, 3, 2),
@@ -257,6 +282,47 @@ def test_emu_mixed_radix_forward(n_fft, win, hop, fmt):
         assert nerr(out, ref) < 3e-6
         mag = E.emu_mr(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_MAG, fmt, fmt, n_warps=nw, fpw=1, n_cta=2)
         assert nerr(mag, np.abs(ref)) < 3e-6
+        # several warps per frame (the launch shape of the large sizes): bit-identical to one warp per frame, the
+        # butterflies are the same, only their assignment to threads differs
+        for nw_g, g in ((4, 2), (8, 8), (16, 16), (8, 4)):
+            grp = E.emu_mr(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_COMPLEX, fmt, fmt, n_warps=nw_g, fpw=1, n_cta=2,
+                           group=g)
+            assert np.array_equal(grp.view(np.float32), out.view(np.float32))
+
+
+@pytest.mark.parametrize('n_fft,hop,n_mels,sr,nw,group,frt', [(400, 160, 80, 16000, 8, 1, 32), (400, 160, 80, 16000, 4, 2, 8),
+                                                                (1000, 250, 128, 22050, 8, 4, 16), (4096, 1024, 128, 44100, 8, 8, 8),
+                                                                (480, 120, 33, 16000, 2, 1, 16), (75, 25, 10, 8000, 4, 1, 32),
+                                                                (1000, 250, 40, 22050, 16, 2, 32)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_emu_mixed_radix_mel_and_db(n_fft, hop, n_mels, sr, nw, group, frt, fmt):
+    """mr_core.cuh fused tail: magnitudes into a (bin x frame) tile, banded filterbank, decibel + per-item maximum --
+    log-mel front ends whose n_fft is not 64 * 2^k (speech: 400 / 160 / 80) in one launch, like the register kernel."""
+    rng = np.random.default_rng(n_mels + n_fft)
+    B = 2
+    x = wave(rng, B, 2, max(3 * n_fft + 700, 2500), fmt)
+    x[1] *= 1e-3
+    w = O.get_window(None, n_fft).astype(np.float32)
+    fb = O.filterbank_mel(sr, n_fft // 2 + 1, n_mels, 0.0, None, False, 'slaney')
+    kw = dict(n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels, input_data_format=fmt, output_data_format=fmt)
+    for pads in ((False, False), (True, True)):
+        ref = O.melspectrogram_layer(x, pad_begin=pads[0], pad_end=pads[1], **kw)
+        out = E.emu_mr(x, n_fft, n_fft, hop, w, pads[0], pads[1], E.MODE_FB, fmt, fmt, n_warps=nw, group=group, fb=fb, frt=frt)
+        assert out.shape == ref.shape and not np.isnan(out).any()
+        assert nerr(out, ref) < 2e-6
+        refdb = O.melspectrogram_layer(x, return_decibel=True, db_dynamic_range=1e9, pad_begin=pads[0], pad_end=pads[1], **kw)
+        outdb, imax = E.emu_mr(x, n_fft, n_fft, hop, w, pads[0], pads[1], E.MODE_FB_DB, fmt, fmt, n_warps=nw, group=group,
+                               fb=fb, frt=frt, with_item_max=True)
+        assert np.abs(outdb - refdb).max() < 5e-5
+        np.testing.assert_allclose(imax, np.maximum(ref.reshape(B, -1).max(1), 1e-5), rtol=2e-6)
+    lin = O.stft_magnitude_layer(x, n_fft, None, hop, input_data_format=fmt, output_data_format=fmt)
+    sm = O.stft_magnitude_layer(x, n_fft, None, hop, return_decibel=True, db_dynamic_range=1e9, input_data_format=fmt,
+                                output_data_format=fmt)
+    smo, imax2 = E.emu_mr(x, n_fft, n_fft, hop, w, False, False, E.MODE_MAG_DB, fmt, fmt, n_warps=nw, group=group, fpw=2,
+                          with_item_max=True)
+    sig = lin > 1e-4 * lin.reshape(B, -1).max(1).reshape(B, 1, 1, 1)
+    assert np.abs(smo - sm)[sig].max() < 1e-3
+    np.testing.assert_allclose(imax2, lin.reshape(B, -1).max(1), rtol=2e-6)
 
 
 def test_emu_mixed_radix_rejects_large_prime_factors():

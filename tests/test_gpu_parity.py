@@ -140,6 +140,48 @@ def test_stft_any_n_fft_mixed_radix(K, n_fft, win, hop, path, fmt):
     assert nerr(mag, np.abs(ref)) < 3e-6
 
 
+@pytest.mark.parametrize('n_fft,hop,n_mels,sr', [(400, 160, 80, 16000), (1000, 250, 128, 22050), (4096, 1024, 128, 44100),
+                                                  (480, 120, 33, 16000), (8192, 2048, 64, 44100)])
+@pytest.mark.parametrize('fmt', ['channels_first', 'channels_last'])
+def test_melspectrogram_fused_any_n_fft(K, n_fft, hop, n_mels, sr, fmt):
+    """Log-mel / dB front ends at n_fft outside 64 * 2^k (speech 400 / 160 / 80; the reference's own n_fft = 1000,
+    tests/test_time_frequency.py:72): ONE mixed-radix launch with the filterbank + decibel tail (+ the clamp pass),
+    equal to the layer-by-layer chain and to the oracle."""
+    rng = np.random.default_rng(n_fft)
+    x = wave(rng, 3, 2, max(9000, 3 * n_fft), fmt)
+    x[1] *= 1e-3
+    kw = dict(n_fft=n_fft, hop_length=hop, sample_rate=sr, n_mels=n_mels, input_data_format=fmt, output_data_format=fmt)
+    xt = torch.from_numpy(x).cuda()
+    n0 = K._native.launch_count()
+    mel = K.get_melspectrogram_layer(**kw)(xt).cpu().numpy()
+    assert K._native.launch_count() - n0 == 1
+    info = K._native.last_launch_info()
+    assert info.startswith('MR ') and 'frt' in info and not info.endswith('frt0'), info
+    ref = O.melspectrogram_layer(x, **kw)
+    assert mel.shape == ref.shape
+    assert nerr(mel, ref) < 3e-6
+    seq = K.get_melspectrogram_layer(**kw)
+    y = xt
+    for layer in seq.layers:
+        y = layer(y)
+    assert nerr(y.cpu().numpy(), ref) < 3e-6
+    n0 = K._native.launch_count()
+    db = K.get_melspectrogram_layer(return_decibel=True, **kw)(xt).cpu().numpy()
+    assert K._native.launch_count() - n0 == 2                       # fused kernel + clamp pass
+    refdb = O.melspectrogram_layer(x, return_decibel=True, **kw)
+    assert np.abs(db - refdb).max() < 2e-4
+    np.testing.assert_allclose(refdb, db, rtol=3e-3, atol=1e-5)
+    # an active clamp (40 dB) and the magnitude-dB tail
+    db40 = K.get_melspectrogram_layer(return_decibel=True, db_dynamic_range=40.0, **kw)(xt).cpu().numpy()
+    assert np.abs(db40 - O.melspectrogram_layer(x, return_decibel=True, db_dynamic_range=40.0, **kw)).max() < 2e-4
+    mdb = K.get_stft_magnitude_layer(n_fft=n_fft, hop_length=hop, return_decibel=True, db_dynamic_range=60.0,
+                                     input_data_format=fmt, output_data_format=fmt)(xt).cpu().numpy()
+    assert K._native.last_launch_info().endswith('frt0')
+    refm = O.stft_magnitude_layer(x, n_fft, None, hop, return_decibel=True, db_dynamic_range=60.0, input_data_format=fmt,
+                                  output_data_format=fmt)
+    assert np.abs(mdb - refm).max() < 2e-3
+
+
 # ------------------------------------------------------------------------------- fused magnitude / mel / dB
 @pytest.mark.parametrize('n_fft,hop,n_mels,sr', [(512, 256, 64, 16000), (1024, 256, 128, 22050), (2048, 512, 128, 44100),
                                                   (256, 128, 20, 8000), (1024, 160, 80, 16000)])

@@ -1,4 +1,4 @@
-"""Runs a few launches of one cfg2 configuration (for ncu).  MODE env: meldb | mel | mag | stft | istft."""
+"""Runs a few launches of one cfg2 configuration (for ncu).  MODE env: meldb | mel | mag | stft | istft | istft_big | music."""
 import os
 import sys
 
@@ -27,6 +27,9 @@ elif mode == 'music':      # n_fft 2048 log-mel: the 16-warp CTA variant
 elif mode == 'istft':
     stft, layer = K.get_perfectly_reconstructing_stft_istft(1024, 256, 'channels_last', 'channels_last')
     x = stft(x[:128, :16000])
+elif mode == 'istft_big':
+    stft, layer = K.get_perfectly_reconstructing_stft_istft(1024, 256, 'channels_last', 'channels_last')
+    x = stft(x)
 for _ in range(n):
     y = layer(x)
 torch.cuda.synchronize()
