@@ -903,6 +903,7 @@ int kapre_stft_supports_mode(const kapre_stft_plan* p, int mode) {
     const int P = (p->n_fft & 1) ? p->n_fft : p->n_fft / 2;
     if (kb_mr_factor(P, radix) < 0 || kb_env_int("KAPRE_B200_NOMR", 0)) return 0;
     int nw, g, b;
+    if (mode == KAPRE_OUT_MAG_DB) return kb_mr_pick(P, p->dev.smem_optin, 228 * 1024, 32, &nw, &g, &b) > 0 ? 1 : 0;
     // 128 bands as the sizing assumption for the filterbank tile (the launch re-picks with the real count and fails loudly)
     return kb_mr_pick(P, p->dev.smem_optin, 228 * 1024, 32, &nw, &g, &b, p->n_fft / 2 + 1, 128, 8) > 0 ? 1 : 0;
 }
@@ -1268,18 +1269,23 @@ int kapre_istft_inverse(const kapre_istft_plan* plan, const void* stft_dev, int 
             if (bps < 1) bps = 1;
             const long long slots = (long long)plan->dev.sm_count * bps;
             const long long hops = (out_len + plan->hop - 1) / plan->hop;
-            int best_m = 0; long long best_cost = 0; int best_seg = 0;
-            const int m_env = kb_env_int("KAPRE_B200_ISTFT2_M", 0);
-            for (int m = 1; m <= 4096; ++m) {
+            // rounds per tile: the most (<= 6: R - 1 halo frames per tile cost <= 6 %) that still leave about one tile per
+            // resident CTA.  Measured (profiles/r2_istft_streaming.md): at B256 x 5 s tiles of 6 rounds beat one wave of 28-round
+            // tiles by 6 % (the static tile walk balances per SM, not per CTA); at B128 x 1 s tiles of 3 rounds (512 tiles on
+            // 592 slots) beat 2 and 4.
+            // Floor: tiles long enough that the halo stays under ~20 % of the frames (hop << win: R is large).
+            int m_lo = (5 * (R - 1) + FR - 1) / FR;
+            if (m_lo < 1) m_lo = 1;
+            const int m_hi = m_lo > 6 ? m_lo : 6;
+            int best_m = m_lo, best_seg = m_lo * FR - (R - 1);
+            for (int m = m_hi; m >= m_lo; --m) {
                 const int seg = m * FR - (R - 1);
-                if (seg < 1) continue;
-                if (m_env > 0 && m != m_env && best_m) continue;
                 const long long nt = (long long)batch * channels * ((hops + seg - 1) / seg);
-                const long long cost = ((nt + slots - 1) / slots) * (2 * m + 1);   // + half a round of per-tile overhead
-                if (!best_m || cost < best_cost || m == m_env) { best_m = m; best_cost = cost; best_seg = seg; }
-                if (m == m_env) break;
-                if (seg >= hops) break;
+                best_m = m; best_seg = seg;
+                if (nt * 100 >= slots * 85) break;
             }
+            const int m_env = kb_env_int("KAPRE_B200_ISTFT2_M", 0);
+            if (m_env > 0 && m_env * FR - (R - 1) >= 1) { best_m = m_env; best_seg = m_env * FR - (R - 1); }
             KbIstftParams p{};
             p.X = (const float2*)stft_dev; p.x_sb = sd->stride_b; p.x_sc = sd->stride_c; p.x_st = sd->stride_t; p.x_sk = sd->stride_f;
             p.B = batch; p.C = channels; p.T = frames; p.n_fft = plan->n_fft; p.hop = plan->hop; p.win = plan->win;

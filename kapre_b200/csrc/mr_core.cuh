@@ -67,14 +67,21 @@ KB_HD KbMrSmem kb_mr_smem_layout(int P, int n_groups, int F = 0, int n_bands = 0
     return s;
 }
 
-// launch shape: the fewest warps per frame (G) that make `want` warps resident per SM (64 registers per thread: 32), given
-// tw + 2 buffers per group; larger G only when nothing smaller reaches the best residency.  Returns warps per SM, 0 if
-// even one group does not fit.
+// launch shape: warps per frame (G) and per CTA (NW) that keep the most warps resident per SM (64 registers per thread:
+// `want` = 32), given tw + 2 buffers per group (+ the filterbank tile).  A group may not be wider than twice the
+// butterflies of its narrowest pass (P / largest radix) -- wider groups are resident but idle; among equals the smaller
+// G wins (loop order).  Returns warps per SM, 0 if nothing fits.
 static inline int kb_mr_pick(int P, int smem_optin, int smem_sm, int want, int* NW_out, int* G_out, int* bps_out,
                              int F = 0, int n_bands = 0, int FRT = 0) {
+    int radix[KB_MR_MAX_PASS];
+    const int np = kb_mr_factor(P, radix);
+    int rmax = 2;
+    for (int i = 0; i < np; ++i) if (radix[i] > rmax) rmax = radix[i];
+    const int gs_max = 2 * (P / rmax) > 32 ? 2 * (P / rmax) : 32;
     int best = 0;
     for (int NW = 8; NW <= 16; NW += 8)
         for (int G = 1; G <= NW; G *= 2) {
+            if (G * 32 > gs_max) continue;
             if (FRT > 0 && (NW / G > FRT || FRT % (NW / G))) continue;     // whole frames per group and tile
             const int smem = kb_mr_smem_layout(P, NW / G, F, n_bands, FRT).total;
             if (smem > smem_optin) continue;

@@ -74,6 +74,7 @@ KB_HD KbStftSmem kb_stft_smem_layout(int Q, int n_fft, int hop, int TF, int n_wa
 struct KbThreadRegs {
     cpx v[32];
     float runmax;
+    cpx aux;          // inverse kernel: prefetched middle bin (lane 0)
 };
 
 #if defined(KB_HOST_EMU)
