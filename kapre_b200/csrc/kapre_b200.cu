@@ -90,6 +90,13 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel_mma(const
     kb_stft_cta<Q, MODE, 1>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
+// variants of the fused filterbank kernel (template bit 1: paired-column pair step, the default for n_fft <= 1024)
+template <int Q, int MODE, int V>
+__global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel_v(const __grid_constant__ KbStftParams p) {
+    extern __shared__ __align__(16) char kb_smem[];
+    kb_stft_cta<Q, MODE, V>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // 16-warp CTAs, one per SM: n_fft = 2048 in the filterbank modes, where an 8-warp CTA already needs more than
 // half of the SM's shared memory (8.4 KB of exchange buffer per warp), so two CTAs never fit
 template <int Q, int MODE>
@@ -361,6 +368,7 @@ struct kapre_stft_plan {
     float cw_a0 = 0.0f;
     float2* twp = nullptr;
     float2* twn = nullptr;
+    float2* twn2 = nullptr;   // kb_make_twn2 (paired-column pair step)
     float* w = nullptr;       // generic path: window[0, win_eff)
     float2* tw = nullptr;     // generic path: exp(-2 pi i r / n_fft)
     int win_eff;
@@ -471,6 +479,9 @@ static int kb_env_int(const char* name, int dflt) {
 // launch configuration of the fused forward kernel
 // ------------------------------------------------------------------------------------------
 struct FwdCfg { int TF, NW, smem, bps; };
+#ifndef KB_PAIRED_DEFAULT
+#define KB_PAIRED_DEFAULT 1
+#endif
 #ifndef KB_FBMMA_DEFAULT
 #define KB_FBMMA_DEFAULT 0
 #endif
@@ -577,6 +588,16 @@ static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStre
         }
     }
     if constexpr (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB) {
+        if constexpr (Q <= 16) {
+            if (!p.fb_mma && (p.variant & 2)) {   // paired-column pair step: the default of the fused filterbank modes
+                int rc = kb_set_smem(kb_stft_kernel_v<Q, MODE, 2>, smem);
+                if (rc) return rc;
+                KbProfScope prof(st);
+                if ((rc = kb_launch_pdl(kb_stft_kernel_v<Q, MODE, 2>, grid, p.n_warps * 32, smem, st, p))) return rc;
+                g_launches++;
+                return 0;
+            }
+        }
         if (p.fb_mma) {
             int rc = kb_set_smem(kb_stft_kernel_mma<Q, MODE>, smem);
             if (rc) return rc;
@@ -844,11 +865,13 @@ int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const floa
     int rc = kb_dev_info(&p->dev);
     if (rc) { delete p; return rc; }
     if (p->Q) {
-        std::vector<float> wh; std::vector<float2> twp, twn;
+        std::vector<float> wh; std::vector<float2> twp, twn, twn2;
         kb_make_wh(window_host, win_length, n_fft, wh);
         kb_make_twp(p->Q, twp);
         kb_make_twn(n_fft, twn);
-        if ((rc = kb_upload(wh, &p->wh)) || (rc = kb_upload(twp, &p->twp)) || (rc = kb_upload(twn, &p->twn))) {
+        kb_make_twn2(n_fft, twn2);
+        if ((rc = kb_upload(wh, &p->wh)) || (rc = kb_upload(twp, &p->twp)) || (rc = kb_upload(twn, &p->twn)) ||
+            (rc = kb_upload(twn2, &p->twn2))) {
             kapre_stft_plan_destroy(p); return rc;
         }
         double ca = 0.0, cb = 0.0;
@@ -879,7 +902,7 @@ int kapre_stft_plan_create(int n_fft, int win_length, int hop_length, const floa
 
 void kapre_stft_plan_destroy(kapre_stft_plan* p) {
     if (!p) return;
-    cudaFree(p->wh); cudaFree(p->cwq); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->w); cudaFree(p->tw);
+    cudaFree(p->wh); cudaFree(p->cwq); cudaFree(p->twp); cudaFree(p->twn); cudaFree(p->twn2); cudaFree(p->w); cudaFree(p->tw);
     cudaFree(p->tc_f1); cudaFree(p->tc_cs); cudaFree(p->tc_csb); cudaFree(p->tc_tw); cudaFree(p->tc_w32);
     delete p;
 }
@@ -1084,6 +1107,10 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     FwdCfg cfg;
     // filterbank phase on the tensor pipe (mma.sync 3xTF32) or on the CUDA cores (chunk lists)
     const int fbmma = (fbmode && fb->mw && kb_env_int("KAPRE_B200_FBMMA", KB_FBMMA_DEFAULT)) ? 1 : 0;
+    // kernel variant of the fused filterbank modes: bit 1 = paired-column pair step (kb_col_dftq_pair_mag; needs two or
+    // more columns per lane, i.e. n_fft <= 1024).  Measured -4.0 % on cfg2 (profiles/r2_small_experiments.md);
+    // KAPRE_B200_PAIRED=0 selects the natural-order pair step for the A/B.
+    const int variant = (fbmode && !fbmma && plan->Q <= 16 && kb_env_int("KAPRE_B200_PAIRED", KB_PAIRED_DEFAULT)) ? 2 : 0;
     if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0,
                          fbmode ? (fbmma ? fb->n_msteps : fb->n_chunks) : 0, fbmma, (long long)B * C, T, &cfg))
         return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
@@ -1093,7 +1120,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     p.B = B; p.C = C; p.L = Ln; p.n_fft = plan->n_fft; p.hop = plan->hop; p.T = T; p.pad_left = pad_left;
     p.x_lo = x_dev; p.x_hi = x_dev + max_off + 1; p.x_numel = max_off + 1;
     p.x_align = (unsigned)(((uintptr_t)x_dev >> 2) & 3); p.bulk_ok = bulk ? 1 : 0; p.dbuf = 0;
-    p.wh = plan->wh; p.twp = plan->twp; p.twn = plan->twn;
+    p.wh = plan->wh; p.twp = plan->twp; p.twn = plan->twn; p.twn2 = plan->twn2;
     p.cosw = plan->cosw; p.cw_a0 = plan->cw_a0; p.cwq = plan->cwq;
     p.out = out_dev; p.o_sb = od->stride_b; p.o_sc = od->stride_c; p.o_st = od->stride_t; p.o_sk = od->stride_f;
     p.mode = mode;
@@ -1158,6 +1185,8 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     } else {
         p.TF = cfg.TF; p.n_tiles_t = (T + cfg.TF - 1) / cfg.TF; p.n_warps = cfg.NW;
         p.fb_mma = fbmma;
+        p.variant = variant;
+
         tiles = (long long)B * C * p.n_tiles_t;
         if (tiles > 0x7fffffffLL) return kb_fail(KAPRE_E_UNSUPPORTED, "too many tiles");
         const long long gmax = (long long)plan->dev.sm_count * cfg.bps;
@@ -1173,8 +1202,9 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     if (rc) return rc;
     {
         char buf[160];
-        snprintf(buf, sizeof(buf), "%sQ%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld fbmma%d", use_mc ? "MC " : "", plan->Q,
-                 cfg.TF, cfg.NW, use_mc ? 0 : (int)bulk, grid, cfg.smem, cfg.bps, tiles, use_mc ? 0 : fbmma);
+        snprintf(buf, sizeof(buf), "%sQ%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld fbmma%d v%d", use_mc ? "MC " : "", plan->Q,
+                 cfg.TF, cfg.NW, use_mc ? 0 : (int)bulk, grid, cfg.smem, cfg.bps, tiles, use_mc ? 0 : fbmma,
+                 (use_mc || !fbmode) ? 0 : p.variant);
         g_launch_info = buf;
     }
     if (dbmode)

@@ -60,6 +60,7 @@ struct KbStftParams {
     const float* wh;
     const float2* twp;
     const float2* twn;
+    const float2* twn2;  // kb_make_twn2: twn for the paired-column pair step (fused filterbank modes)
     // cosine-sum windows (hann, hamming, ... with win_length == n_fft): 0.5*w[n] = cw_a0 - B cos(2 pi n / n_fft)
     // is evaluated in registers instead of loaded: cwq[q] = B * (cos a_e, cos a_o, sin a_e, sin a_o) with
     // a_e = 2 pi (2q) / n_fft, a_o = 2 pi (2q + 1) / n_fft; the other factor exp(2 pi i j / 32) is a constant.
@@ -84,6 +85,7 @@ struct KbStftParams {
     int n_chunks;
     // two-level form (kb_make_fb_band_desc): fb_bands = 1 makes the single-channel kernel walk band descriptors
     int fb_bands;
+    int variant;         // experimental kernel variants of the fused filterbank modes (bit 1: paired-column pair step)
     const kb_i2* bd;
     const int* bg;
     int n_bd;
@@ -239,6 +241,17 @@ KB_HD float kb_max_keepnan(float a, float b) {
     uint32_t ua, ub;
     std::memcpy(&ua, &a, 4); std::memcpy(&ub, &b, 4);
     return ua > ub ? a : b;
+#endif
+}
+
+// log2 of a power of two
+KB_HD int kb_ilog2(int v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs(v) - 1;
+#else
+    int r = 0;
+    while ((1 << r) < v) ++r;
+    return r;
 #endif
 }
 

@@ -19,16 +19,24 @@ static inline int kb_q_for_nfft(int n_fft) {
     }
 }
 
-// exp(-2 pi i q k1 / P), row stride 33 (bank-conflict padding)
+// exp(-2 pi i q k1 / P), row stride 33 (bank-conflict padding).
+// Entry [q][0] is 1 mathematically and no kernel multiplies by it in the ordinary transpose (ex[0] = v[0]); the
+// paired-column variant of the fused kernel (kb_col_dftq_pair_mag) does: it holds exp(-2 pi i s q / Q), s = Q/2 + 1,
+// which shifts the spectrum of column k1 = 0 cyclically by s so that lane 0's self-paired column lines up with the
+// register pattern of the other lanes.
 static inline void kb_make_twp(int Q, std::vector<float2>& out) {
     const int P = 32 * Q;
     out.assign((size_t)Q * 33, make_float2(1.0f, 0.0f));
-    for (int q = 0; q < Q; ++q)
-        for (int k1 = 0; k1 < 32; ++k1) {
+    for (int q = 0; q < Q; ++q) {
+        for (int k1 = 1; k1 < 32; ++k1) {
             const int r = (q * k1) % P;
             const double a = -2.0 * M_PI * (double)r / (double)P;
             out[(size_t)q * 33 + k1] = make_float2((float)std::cos(a), (float)std::sin(a));
         }
+        const int r0 = ((Q / 2 + 1) * q) % Q;
+        const double a0 = -2.0 * M_PI * (double)r0 / (double)Q;
+        out[(size_t)q * 33] = make_float2((float)std::cos(a0), (float)std::sin(a0));
+    }
 }
 
 // exp(-2 pi i k / n_fft), k = 0 .. n_fft/4 - 1
@@ -39,6 +47,13 @@ static inline void kb_make_twn(int n_fft, std::vector<float2>& out) {
         const double a = -2.0 * M_PI * (double)k / (double)n_fft;
         out[k] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
+}
+
+// The same table for the paired-column pair step: entries k = 0 (mod 32) are only read by lane 0's self-paired
+// column k1 = 0, through the code path that multiplies by -i (bins >= P/2 of the other lanes), so they hold i W^k.
+static inline void kb_make_twn2(int n_fft, std::vector<float2>& out) {
+    kb_make_twn(n_fft, out);
+    for (size_t k = 0; k < out.size(); k += 32) out[k] = make_float2(-out[k].y, out[k].x);
 }
 
 // 0.5 * analysis window, right zero-padded (win < n_fft) or cropped (win > n_fft) to n_fft:

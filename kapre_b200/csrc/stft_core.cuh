@@ -321,7 +321,7 @@ KB_HD void kb_store_vec(float* dst, const float* src) {
 // Step 1: window the frame at `fr`, 32-point DFTs over z[q + Q j], twiddle, store transposed (32 x 33).
 //   wmode 2: cosine-sum window evaluated in registers (KbStftParams::cwq), samples read as aligned pairs
 //   wmode 1: window table, aligned pairs;  wmode 0: window table, scalar loads (odd sample offset)
-template <int Q>
+template <int Q, bool TW0 = false>
 KB_FN void kb_col_window_dft32(KbThreadRegs& R, const float* fr, const float* __restrict__ wh_s,
                                const kb_f4* __restrict__ cwq_s, float cw_a0, const cpx* __restrict__ twp_s,
                                cpx* region, int g, int q, int wmode) {
@@ -359,7 +359,7 @@ KB_FN void kb_col_window_dft32(KbThreadRegs& R, const float* fr, const float* __
     kb_fft_dif<32>(R.v);
     cpx* ex = region + (g * Q + q) * 33;
     const cpx* tw = twp_s + q * 33;
-    ex[0] = R.v[0];
+    ex[0] = TW0 ? cmul(R.v[0], tw[0]) : R.v[0];   // TW0: spectrum shift of column 0 for the paired-column form (kb_make_twp)
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) ex[k1] = cmul(R.v[kb_brev<32>(k1)], tw[k1]);
 }
@@ -388,6 +388,90 @@ KB_FN void kb_col_dftq_store(KbThreadRegs& R, cpx* region, int g, int q, int zst
         const int k1 = q + Q * i;
 #pragma unroll
         for (int k2 = 0; k2 < Q; ++k2) zs[k1 + 32 * k2] = R.v[i * Q + kb_brev<Q>(k2)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Paired-column form of steps 2-4 for the fused filterbank modes (Q <= 16, i.e. two or more columns per lane).
+// The real-FFT pair step combines Z[k] with Z[P - k]; with k = k1 + 32 k2 the partner of column k1 is column
+// 32 - k1.  Dealing the columns so that lane q owns BOTH k1 = r and k1 = 32 - r (r = q + Q u, u < 16 / Q) keeps every
+// pair inside one lane: the natural-order store, its re-read and the register parking of the magnitudes disappear
+// (2 of the 5 trips of a spectrum through shared memory), and the magnitudes go straight to [bin][frame].
+// The two self-paired columns k1 = 0 and k1 = 16 form lane 0's first pair; there the partners sit inside one column,
+// which costs Q complex selects: column 16 is loaded as `a`, column 0 as `b`, pre-shifted cyclically by s = Q/2 + 1
+// (a modulation folded into the twiddle table, kb_make_twp) so that slot i pairs
+//     i <  Q/2:  A = a[i]      (bin 16 + 32 i),      B = a[Q-1-i]   (instead of b[Q-1-i])
+//     i >= Q/2:  A = b'[i-1]   (bin 32 (i - Q/2)),   B = b'[Q-1-i]  (the generic register)
+// and b'[Q-1] is the middle bin P/2.  Slots i >= Q/2 are bins >= P/2: W^k = -i W^(k - P/2), table twn2 (kb_make_twn2).
+// ------------------------------------------------------------------------------------------
+KB_HD cpx csel(bool c, cpx a, cpx b) { return cmake(c ? a.re : b.re, c ? a.im : b.im); }
+
+template <int Q>
+KB_FN void kb_col_gather_paired(KbThreadRegs& R, const cpx* region, int g, int q) {
+    constexpr int CP = 16 / Q;   // column pairs per lane
+    const cpx* ex = region + (g * Q) * 33;
+#pragma unroll
+    for (int u = 0; u < CP; ++u) {
+        const int r = q + Q * u;
+        const int kA = (r == 0) ? 16 : r, kB = (r == 0) ? 0 : 32 - r;
+#pragma unroll
+        for (int q2 = 0; q2 < Q; ++q2) {
+            R.v[(2 * u) * Q + q2] = ex[q2 * 33 + kA];
+            R.v[(2 * u + 1) * Q + q2] = ex[q2 * 33 + kB];
+        }
+    }
+}
+
+// Q-point DFTs of the lane's column pairs, pair step, magnitudes -> mw[bin * FPW + g] (the warp's own region).
+template <int Q>
+KB_FN void kb_col_dftq_pair_mag(KbThreadRegs& R, const cpx* __restrict__ twn2_s, float* mw, int g, int q) {
+    constexpr int FPW = 32 / Q, CP = 16 / Q, P = 32 * Q, H = Q / 2;
+#pragma unroll
+    for (int u = 0; u < CP; ++u) {
+        cpx* a = R.v + (2 * u) * Q;
+        cpx* b = R.v + (2 * u + 1) * Q;
+        kb_fft_dif<Q>(a);
+        kb_fft_dif<Q>(b);
+        const int r = q + Q * u;
+        const bool sp = (u == 0) && (q == 0);      // the self-paired columns
+        const int kLo = sp ? 16 : r;               // slot i < H:  bin kLo + 32 i
+        const int kHi = sp ? -(P / 2) : r;         // slot i >= H: bin kHi + 32 i
+        const int tHi = sp ? 0 : r;                // twiddle index of slot i >= H: tHi + 32 i - P/2
+        float* mg = mw + g;                        // magnitude of bin k at mw[k * FPW + g], its mirror image at P - k
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            cpx A, Bv;
+            if (i < H) {
+                A = a[kb_brev<Q>(i)];
+                Bv = (u == 0) ? csel(sp, a[kb_brev<Q>(Q - 1 - i)], b[kb_brev<Q>(Q - 1 - i)]) : b[kb_brev<Q>(Q - 1 - i)];
+            } else {
+                A = (u == 0) ? csel(sp, b[kb_brev<Q>(i - 1)], a[kb_brev<Q>(i)]) : a[kb_brev<Q>(i)];
+                Bv = b[kb_brev<Q>(Q - 1 - i)];
+            }
+            const cpx E = cadd_conj(A, Bv);            // A + conj(B)
+            const cpx D = csub_conj(A, Bv);            // A - conj(B)
+            cpx X1, X2;
+            if (i < H) {
+                const cpx T = cmul(cmake(D.im, -D.re), twn2_s[kLo + 32 * i]);   // W^k (-i D)
+                X1 = cadd(E, T);
+                X2 = csub(E, T);
+            } else {
+                const cpx G = cmul(D, twn2_s[tHi + (32 * i - P / 2)]);                    // W^k (-i D) = -W^(k - P/2) D
+                X1 = csub(E, G);
+                X2 = cadd(E, G);
+            }
+            const float m1 = kb_sqrt(cnorm(X1));
+            const float m2 = kb_sqrt(cnorm(X2));
+            const int k = (i < H ? kLo : kHi) + 32 * i;
+            mg[k * FPW] = m1;
+            mg[(P - k) * FPW] = m2;
+        }
+        if (u == 0) {
+            if (sp) {   // bin P/2 pairs with itself
+                const cpx A = b[kb_brev<Q>(Q - 1)];
+                mw[(P / 2) * FPW + g] = kb_sqrt(cnorm(cmake(2.0f * A.re, -2.0f * A.im)));
+            }
+        }
     }
 }
 
@@ -556,7 +640,9 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     const int H = p.hop, N = p.n_fft, TF = p.TF;
     // filterbank phase on the tensor pipe (kb_fb_mma_phase): a separate instantiation, measured slower than the
     // CUDA-core chunk lists (profiles/r2_fbmma_ab.md), kept selectable for the A/B
-    constexpr bool fbmma = fbmode && FBMMA != 0;
+    constexpr bool fbmma = fbmode && (FBMMA & 1) != 0;
+    // paired-column pair step (kb_col_dftq_pair_mag): FBMMA bit 1
+    constexpr bool paired = fbmode && (FBMMA & 2) != 0 && FPW >= 2;
     const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, fbmma ? p.n_msteps : p.n_chunks,
                                              fbmma ? 1 : 0);
     float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
@@ -589,7 +675,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
         if (tid == 0) kb_bar_init(bar, 1);
         for (int i = tid; i < N; i += kb_nt) wh_s[i] = p.wh[i];
         for (int i = tid; i < Q * 33; i += kb_nt) { float2 t = p.twp[i]; twp_s[i] = cmake(t.x, t.y); }
-        for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
+        for (int i = tid; i < P / 2; i += kb_nt) { float2 t = paired ? p.twn2[i] : p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
         if (p.cosw) { for (int i = tid; i < Q; i += kb_nt) cwq_s[i] = p.cwq[i]; }
         if (fbmma) {
             for (int i = tid; i < p.n_msteps; i += kb_nt) cm_s[i] = p.ms[i];
@@ -660,8 +746,8 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int g = lane / Q, q = lane % Q;
                 const int col = round * FR + warp * FPW + g;
                 if (col < TF)
-                    kb_col_window_dft32<Q>(R, smp_s + col * H, wh_s, cwq_s, p.cw_a0, twp_s, ex_s + warp * EXS, g, q,
-                                           even_base ? (p.cosw ? 2 : 1) : 0);
+                    kb_col_window_dft32<Q, paired>(R, smp_s + col * H, wh_s, cwq_s, p.cw_a0, twp_s, ex_s + warp * EXS, g, q,
+                                                   even_base ? (p.cosw ? 2 : 1) : 0);
             KB_PHASE_END
             if (round == n_rounds - 1 && !fbmode) {
                 // every warp has consumed the sample buffer: fetch the next tile behind phases 2-4
@@ -676,6 +762,27 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
             } else {
                 KB_SYNC_WARP;
             }
+            if constexpr (paired) {
+                // ---- phases 2-4, paired-column form: both members of every pair (k, P - k) in one lane --------
+                KB_PHASE_BEGIN
+                    const int warp = tid >> 5, lane = tid & 31;
+                    const int g = lane / Q, q = lane % Q;
+                    const int col = round * FR + warp * FPW + g;
+                    if (col < TF) kb_col_gather_paired<Q>(R, ex_s + warp * EXS, g, q);
+                KB_PHASE_END
+                KB_SYNC_WARP;
+                KB_PHASE_BEGIN
+                    const int warp = tid >> 5, lane = tid & 31;
+                    const int g = lane / Q, q = lane % Q;
+                    const int col = round * FR + warp * FPW + g;
+                    float* mw = reinterpret_cast<float*>(ex_s + warp * EXS);
+                    if (col < TF) kb_col_dftq_pair_mag<Q>(R, twn_s, mw, g, q);
+                    if (lane < 3) {   // pad bins: chunks of 4 bins read past bin P
+#pragma unroll
+                        for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;
+                    }
+                KB_PHASE_END
+            } else {
             // ---- phase 2: gather this lane's columns --------------------------------------
             KB_PHASE_BEGIN
                 const int warp = tid >> 5, lane = tid & 31;
@@ -804,6 +911,7 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                     }
                 KB_PHASE_END
             }
+            }
         }  // rounds
 
         if (fbmode) {
@@ -866,9 +974,9 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
             } else {
             KB_PHASE_BEGIN
                 (void)R;
-                const int warp = tid >> 5, lane = tid & 31;
-                const int w = lane % NW;
-                const int grp = warp * (32 / NW) + lane / NW;           // 0..31
+                // NW is a power of two (kb_pick_fwd_cfg): lane group = tid / NW, lane within the group = tid % NW
+                const int w = tid & (NW - 1);
+                const int grp = tid >> kb_ilog2(NW);                    // 0..31
                 const float* __restrict__ mw = reinterpret_cast<const float*>(ex_s + w * EXS);
                 float* __restrict__ ocol = out_s + (w * FPW) * L.Mp;
                 float a0[FPW], a1[FPW];

@@ -25,6 +25,7 @@ static void run_stft_qm(const KbStftParams& p, int n_cta) {
         std::fill(raw.begin(), raw.end(), (char)0x7f);  // poison: catches reads of unwritten smem
         if constexpr (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB) {
             if (fbm) { kb_stft_cta<Q, MODE, 1>(p, smem, cta, n_cta); continue; }
+            if (p.variant & 2) { kb_stft_cta<Q, MODE, 2>(p, smem, cta, n_cta); continue; }
         }
         kb_stft_cta<Q, MODE>(p, smem, cta, n_cta);
     }
@@ -110,18 +111,21 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     if ((mode == KB_OUT_FB || mode == KB_OUT_FB_DB) && TF != n_warps * (32 / Q)) return -2;  // kernel contract
     if (TF % (32 / Q)) return -2;
     std::vector<float> wh;
-    std::vector<float2> twp, twn;
+    std::vector<float2> twp, twn, twn2;
     std::vector<KbBand> bands;
     std::vector<float> fbw;
     std::vector<kb_f4> cw; std::vector<kb_i2> cm; std::vector<int> cg;
     kb_make_wh(window, win_length, n_fft, wh);
     kb_make_twp(Q, twp);
     kb_make_twn(n_fft, twn);
+    kb_make_twn2(n_fft, twn2);
+    // fb_mma argument: bit 0 tensor-core filterbank, bit 1 band descriptors, bit 2 paired-column pair step (kernel variant 2)
+    const int variant = (fb_mma >> 1) & 2;
     if (fb) { kb_make_bands(fb, n_freq, n_bands, bands, fbw); kb_make_fb_chunks(fb, n_freq, n_bands, 32, cw, cm, cg); }
     KbStftParams p{};
     p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
     p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left;
-    p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data();
+    p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data(); p.twn2 = twn2.data();
     std::vector<kb_f4> cwq;
     {
         double ca = 0.0, cb = 0.0;
@@ -133,12 +137,13 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     p.out = out; p.o_sb = o_sb; p.o_sc = o_sc; p.o_st = o_st; p.o_sk = o_sk; p.mode = mode;
     p.bands = fb ? bands.data() : nullptr; p.fbw = fb ? fbw.data() : nullptr; p.n_bands = fb ? n_bands : 0;
     p.n_fbw = fb ? (int)fbw.size() : 0;
-    if (fb) { p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cw.size(); }
+    if (fb) { p.cw = cw.data(); p.cm = cm.data(); p.cg = cg.data(); p.n_chunks = (int)cm.size(); }
     std::vector<kb_i2> bd; std::vector<int> bg;
     if (fb && (fb_mma & 2)) {          // bit 1: two-level band-descriptor walk of the chunk lists
         kb_make_fb_band_desc(cm, cg, 32, bd, bg);
         p.fb_bands = 1; p.bd = bd.data(); p.bg = bg.data(); p.n_bd = (int)bd.size();
     }
+    p.variant = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB) ? variant : 0;
     fb_mma &= 1;
     std::vector<kb_f4> mw; std::vector<kb_i2> ms; std::vector<int> mg;
     if (fb && fb_mma) {

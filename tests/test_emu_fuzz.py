@@ -118,7 +118,7 @@ def test_fuzz_filterbank_modes(n_fft, hop, L, C, n_mels, htk, pad_end, ifmt, ofm
                                       TF=(nw * fpw) // C, n_warps=nw, n_cta=1 + seed % 3)
     else:
         out, item_max = E.emu_stft(x, n_fft, n_fft, hop, w, False, pad_end, E.MODE_FB_DB, ifmt, ofmt, fb=fb,
-                                   TF=nw * fpw, n_warps=nw, n_cta=1 + seed % 3, bulk=seed % 2, fb_mma=(seed // 2) % 3)   # 0 flat chunk lists, 1 tensor-core GEMM, 2 band descriptors
+                                   TF=nw * fpw, n_warps=nw, n_cta=1 + seed % 3, bulk=seed % 2, fb_mma=(0, 1, 2, 4)[(seed // 2) % 4])   # flat chunk lists, tensor-core GEMM, band descriptors, paired-column pair step
     assert out.shape == ref.shape
     ref_db = 10.0 * np.log10(np.maximum(ref, 1e-5))
     assert np.abs(out - ref_db).max() < 2e-3

@@ -65,6 +65,10 @@ def test_emu_mel_and_db(n_fft, hop, n_mels, sr, TF, nw, fmt):
     # two-level walk over band descriptors: the same sums in the same order -> bit-identical
     out2, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw, fb_mma=2)
     assert np.array_equal(out, out2)
+    # paired-column pair step (kb_col_dftq_pair_mag): same magnitudes up to the rounding of the twiddles of bins >= P/2
+    out3, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw, fb_mma=4)
+    assert nerr(out3, ref) < 1e-6
+    assert nerr(out3, out) < 3e-7
     refdb = O.melspectrogram_layer(x, return_decibel=True, db_dynamic_range=1e9, **kw)
     outdb, imax = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB_DB, fmt, fmt, fb=fb, TF=TF, n_warps=nw)
     assert np.abs(outdb - refdb).max() < 5e-5
