@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel_mma(const
     kb_stft_cta<Q, MODE, 1>(p, kb_smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
-// variants of the fused filterbank kernel (template bit 1: paired-column pair step, the default for n_fft <= 1024)
+// the A/B alternative of the pair step (template bit 1: natural-order pair step instead of the paired-column form)
 template <int Q, int MODE, int V>
 __global__ void __launch_bounds__(KB_MAX_WARPS * 32, 2) kb_stft_kernel_v(const __grid_constant__ KbStftParams p) {
     extern __shared__ __align__(16) char kb_smem[];
@@ -587,17 +587,17 @@ static int kb_launch_stft_qm(const KbStftParams& p, int grid, int smem, cudaStre
             return kb_fail(KAPRE_E_UNSUPPORTED, "no 16-warp instantiation for Q=%d mode=%d", Q, MODE);
         }
     }
-    if constexpr (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB) {
-        if constexpr (Q <= 16) {
-            if (!p.fb_mma && (p.variant & 2)) {   // paired-column pair step: the default of the fused filterbank modes
-                int rc = kb_set_smem(kb_stft_kernel_v<Q, MODE, 2>, smem);
-                if (rc) return rc;
-                KbProfScope prof(st);
-                if ((rc = kb_launch_pdl(kb_stft_kernel_v<Q, MODE, 2>, grid, p.n_warps * 32, smem, st, p))) return rc;
-                g_launches++;
-                return 0;
-            }
+    if constexpr (Q == 16) {
+        if (p.variant & 2) {   // the other form of the pair step (KAPRE_B200_PAIRED=0): the A/B alternative, n_fft 1024 only
+            int rc = kb_set_smem(kb_stft_kernel_v<Q, MODE, 2>, smem);
+            if (rc) return rc;
+            KbProfScope prof(st);
+            if ((rc = kb_launch_pdl(kb_stft_kernel_v<Q, MODE, 2>, grid, p.n_warps * 32, smem, st, p))) return rc;
+            g_launches++;
+            return 0;
         }
+    }
+    if constexpr (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB) {
         if (p.fb_mma) {
             int rc = kb_set_smem(kb_stft_kernel_mma<Q, MODE>, smem);
             if (rc) return rc;
@@ -1107,10 +1107,10 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
     FwdCfg cfg;
     // filterbank phase on the tensor pipe (mma.sync 3xTF32) or on the CUDA cores (chunk lists)
     const int fbmma = (fbmode && fb->mw && kb_env_int("KAPRE_B200_FBMMA", KB_FBMMA_DEFAULT)) ? 1 : 0;
-    // kernel variant of the fused filterbank modes: bit 1 = paired-column pair step (kb_col_dftq_pair_mag; needs two or
-    // more columns per lane, i.e. n_fft <= 1024).  Measured -4.0 % on cfg2 (profiles/r2_small_experiments.md);
-    // KAPRE_B200_PAIRED=0 selects the natural-order pair step for the A/B.
-    const int variant = (fbmode && !fbmma && plan->Q <= 16 && kb_env_int("KAPRE_B200_PAIRED", KB_PAIRED_DEFAULT)) ? 2 : 0;
+    // Pair step of the register kernel: kb_stft_cta picks the paired-column or the natural-order form per (n_fft, mode) from
+    // the measurements in profiles/r2_small_experiments.md; KAPRE_B200_PAIRED=0 runs the other form (variant bit 1,
+    // instantiated for n_fft 1024 only: the A/B alternative).
+    const int variant = (!fbmma && plan->Q == 16 && kb_env_int("KAPRE_B200_PAIRED", KB_PAIRED_DEFAULT) == 0) ? 2 : 0;
     if (!kb_pick_fwd_cfg(plan->dev, plan->Q, plan->n_fft, plan->hop, mode, fbmode ? fb->n_bands : 0,
                          fbmode ? (fbmma ? fb->n_msteps : fb->n_chunks) : 0, fbmma, (long long)B * C, T, &cfg))
         return kb_fail(KAPRE_E_UNSUPPORTED, "no launch configuration fits shared memory (n_fft=%d hop=%d bands=%d)",
@@ -1204,7 +1204,7 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
         char buf[160];
         snprintf(buf, sizeof(buf), "%sQ%d TF%d NW%d bulk%d grid%d smem%d bps%d tiles%lld fbmma%d v%d", use_mc ? "MC " : "", plan->Q,
                  cfg.TF, cfg.NW, use_mc ? 0 : (int)bulk, grid, cfg.smem, cfg.bps, tiles, use_mc ? 0 : fbmma,
-                 (use_mc || !fbmode) ? 0 : p.variant);
+                 use_mc ? 0 : p.variant);
         g_launch_info = buf;
     }
     if (dbmode)

@@ -85,7 +85,7 @@ struct KbStftParams {
     int n_chunks;
     // two-level form (kb_make_fb_band_desc): fb_bands = 1 makes the single-channel kernel walk band descriptors
     int fb_bands;
-    int variant;         // experimental kernel variants of the fused filterbank modes (bit 1: paired-column pair step)
+    int variant;         // bit 1: natural-order pair step instead of the paired-column form (A/B alternative)
     const kb_i2* bd;
     const int* bg;
     int n_bd;

@@ -422,10 +422,11 @@ KB_FN void kb_col_gather_paired(KbThreadRegs& R, const cpx* region, int g, int q
     }
 }
 
-// Q-point DFTs of the lane's column pairs, pair step, magnitudes -> mw[bin * FPW + g] (the warp's own region).
-template <int Q>
-KB_FN void kb_col_dftq_pair_mag(KbThreadRegs& R, const cpx* __restrict__ twn2_s, float* mw, int g, int q) {
-    constexpr int FPW = 32 / Q, CP = 16 / Q, P = 32 * Q, H = Q / 2;
+// Q-point DFTs of the lane's column pairs and the pair step; emit(k, X, cj) receives bin k of the frame: X[k] = X, or
+// conj(X) when cj (the mirror image P - k of a slot).
+template <int Q, class Emit>
+KB_FN void kb_col_dftq_pair(KbThreadRegs& R, const cpx* __restrict__ twn2_s, int q, Emit emit) {
+    constexpr int CP = 16 / Q, P = 32 * Q, H = Q / 2;
 #pragma unroll
     for (int u = 0; u < CP; ++u) {
         cpx* a = R.v + (2 * u) * Q;
@@ -437,7 +438,6 @@ KB_FN void kb_col_dftq_pair_mag(KbThreadRegs& R, const cpx* __restrict__ twn2_s,
         const int kLo = sp ? 16 : r;               // slot i < H:  bin kLo + 32 i
         const int kHi = sp ? -(P / 2) : r;         // slot i >= H: bin kHi + 32 i
         const int tHi = sp ? 0 : r;                // twiddle index of slot i >= H: tHi + 32 i - P/2
-        float* mg = mw + g;                        // magnitude of bin k at mw[k * FPW + g], its mirror image at P - k
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
             cpx A, Bv;
@@ -456,23 +456,29 @@ KB_FN void kb_col_dftq_pair_mag(KbThreadRegs& R, const cpx* __restrict__ twn2_s,
                 X1 = cadd(E, T);
                 X2 = csub(E, T);
             } else {
-                const cpx G = cmul(D, twn2_s[tHi + (32 * i - P / 2)]);                    // W^k (-i D) = -W^(k - P/2) D
+                const cpx G = cmul(D, twn2_s[tHi + (32 * i - P / 2)]);          // W^k (-i D) = -W^(k - P/2) D
                 X1 = csub(E, G);
                 X2 = cadd(E, G);
             }
-            const float m1 = kb_sqrt(cnorm(X1));
-            const float m2 = kb_sqrt(cnorm(X2));
             const int k = (i < H ? kLo : kHi) + 32 * i;
-            mg[k * FPW] = m1;
-            mg[(P - k) * FPW] = m2;
+            emit(k, X1, false);
+            emit(P - k, X2, true);                     // X2 = conj(X[P - k])
         }
         if (u == 0) {
             if (sp) {   // bin P/2 pairs with itself
                 const cpx A = b[kb_brev<Q>(Q - 1)];
-                mw[(P / 2) * FPW + g] = kb_sqrt(cnorm(cmake(2.0f * A.re, -2.0f * A.im)));
+                emit(P / 2, cmake(2.0f * A.re, -2.0f * A.im), false);
             }
         }
     }
+}
+
+// fused filterbank modes: magnitudes -> mw[bin * FPW + g] (the warp's own exchange region, layout [bin][frame-in-warp])
+template <int Q>
+KB_FN void kb_col_dftq_pair_mag(KbThreadRegs& R, const cpx* __restrict__ twn2_s, float* mw, int g, int q) {
+    constexpr int FPW = 32 / Q;
+    float* mg = mw + g;
+    kb_col_dftq_pair<Q>(R, twn2_s, q, [&](int k, cpx X, bool) { mg[k * FPW] = kb_sqrt(cnorm(X)); });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -641,8 +647,13 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     // filterbank phase on the tensor pipe (kb_fb_mma_phase): a separate instantiation, measured slower than the
     // CUDA-core chunk lists (profiles/r2_fbmma_ab.md), kept selectable for the A/B
     constexpr bool fbmma = fbmode && (FBMMA & 1) != 0;
-    // paired-column pair step (kb_col_dftq_pair_mag): FBMMA bit 1
-    constexpr bool paired = fbmode && (FBMMA & 2) != 0 && FPW >= 2;
+    // Pair step: the paired-column form (kb_col_dftq_pair) whenever a lane owns two or more columns (n_fft <= 1024), except
+    // where its output pattern costs more than the shared-memory trips it saves: a lane then writes bins q + 32 i, i.e. runs
+    // of Q consecutive bins per frame instead of 32 -- measured on B256 x 5 s (profiles/r2_small_experiments.md): complex
+    // output n_fft 512 / 256 +31 % / +68 % (store-bound modes), magnitude + phase n_fft 256 +5 %, everything else -1 ... -11 %.
+    // FBMMA bit 1 selects the other form (the A/B alternative).
+    constexpr bool prefer_natural = (MODE == KB_OUT_COMPLEX && Q < 16) || (MODE == KB_OUT_MAG_PHASE && Q == 4);
+    constexpr bool paired = FPW >= 2 && !fbmma && (((FBMMA & 2) != 0) == prefer_natural);
     const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, fbmma ? p.n_msteps : p.n_chunks,
                                              fbmma ? 1 : 0);
     float* __restrict__ wh_s = reinterpret_cast<float*>(smem + L.wh);
@@ -770,18 +781,47 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                     const int col = round * FR + warp * FPW + g;
                     if (col < TF) kb_col_gather_paired<Q>(R, ex_s + warp * EXS, g, q);
                 KB_PHASE_END
-                KB_SYNC_WARP;
+                KB_SYNC_WARP;   // every lane has its columns: the region may be overwritten (magnitudes / next round)
                 KB_PHASE_BEGIN
                     const int warp = tid >> 5, lane = tid & 31;
                     const int g = lane / Q, q = lane % Q;
                     const int col = round * FR + warp * FPW + g;
-                    float* mw = reinterpret_cast<float*>(ex_s + warp * EXS);
-                    if (col < TF) kb_col_dftq_pair_mag<Q>(R, twn_s, mw, g, q);
-                    if (lane < 3) {   // pad bins: chunks of 4 bins read past bin P
+                    if constexpr (fbmode) {
+                        float* mw = reinterpret_cast<float*>(ex_s + warp * EXS);
+                        if (col < TF) kb_col_dftq_pair_mag<Q>(R, twn_s, mw, g, q);
+                        if (lane < 3) {   // pad bins: chunks of 4 bins read past bin P
 #pragma unroll
-                        for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;
+                            for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;
+                        }
+                    } else {
+                        const int t = t0 + col;
+                        if (col < TF && t < p.T) {
+                            const long long ofr = obase + (long long)t * p.o_st;
+                            const int sk = (int)p.o_sk;
+                            float2* oc = reinterpret_cast<float2*>(p.out) + ofr;
+                            float* orl = reinterpret_cast<float*>(p.out) + ofr;
+                            float rmax = R.runmax;
+                            kb_col_dftq_pair<Q>(R, twn_s, q, [&](int k, cpx X, bool cj) {
+                                if (MODE == KB_OUT_COMPLEX) {
+                                    const float2 v = make_float2(X.re, cj ? -X.im : X.im);
+                                    if (sk == 1) oc[k] = v; else oc[k * sk] = v;
+                                } else {
+                                    float m = kb_sqrt(cnorm(X));
+                                    if (MODE == KB_OUT_MAG_PHASE)   // tf.math.angle, kapre/time_frequency.py:402
+                                        orl[(long long)k * sk + p.ph_off] = kb_atan2(cj ? -X.im : X.im, X.re);
+                                    if (dbany) {
+                                        m = kb_floor_keepnan(m, p.amin);
+                                        rmax = kb_max_keepnan(rmax, m);
+                                        m = p.db_mul * kb_log2(m) - p.db_sub;
+                                    }
+                                    if (sk == 1) orl[k] = m; else orl[k * sk] = m;
+                                }
+                            });
+                            R.runmax = rmax;
+                        }
                     }
                 KB_PHASE_END
+                if (!fbmode) { KB_SYNC_WARP; }
             } else {
             // ---- phase 2: gather this lane's columns --------------------------------------
             KB_PHASE_BEGIN

@@ -25,8 +25,8 @@ static void run_stft_qm(const KbStftParams& p, int n_cta) {
         std::fill(raw.begin(), raw.end(), (char)0x7f);  // poison: catches reads of unwritten smem
         if constexpr (MODE == KB_OUT_FB || MODE == KB_OUT_FB_DB) {
             if (fbm) { kb_stft_cta<Q, MODE, 1>(p, smem, cta, n_cta); continue; }
-            if (p.variant & 2) { kb_stft_cta<Q, MODE, 2>(p, smem, cta, n_cta); continue; }
         }
+        if (p.variant & 2) { kb_stft_cta<Q, MODE, 2>(p, smem, cta, n_cta); continue; }
         kb_stft_cta<Q, MODE>(p, smem, cta, n_cta);
     }
 }
@@ -119,7 +119,8 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
     kb_make_twp(Q, twp);
     kb_make_twn(n_fft, twn);
     kb_make_twn2(n_fft, twn2);
-    // fb_mma argument: bit 0 tensor-core filterbank, bit 1 band descriptors, bit 2 paired-column pair step (kernel variant 2)
+    // fb_mma argument: bit 0 tensor-core filterbank, bit 1 band descriptors, bit 2 natural-order pair step (kernel variant 2;
+    // the default is the paired-column form)
     const int variant = (fb_mma >> 1) & 2;
     if (fb) { kb_make_bands(fb, n_freq, n_bands, bands, fbw); kb_make_fb_chunks(fb, n_freq, n_bands, 32, cw, cm, cg); }
     KbStftParams p{};
@@ -143,7 +144,7 @@ int kb_emu_stft(const float* x, long long x_sb, long long x_sc, long long x_sl, 
         kb_make_fb_band_desc(cm, cg, 32, bd, bg);
         p.fb_bands = 1; p.bd = bd.data(); p.bg = bg.data(); p.n_bd = (int)bd.size();
     }
-    p.variant = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB) ? variant : 0;
+    p.variant = variant;
     fb_mma &= 1;
     std::vector<kb_f4> mw; std::vector<kb_i2> ms; std::vector<int> mg;
     if (fb && fb_mma) {

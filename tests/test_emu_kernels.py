@@ -29,6 +29,10 @@ def test_emu_stft_complex_and_mag(n_fft, hop, win, fmt, pads):
     assert nerr(out, ref) < 1e-6
     mag, _ = E.emu_stft(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_MAG, fmt, fmt, TF=8, n_warps=2, dbuf=0)
     assert nerr(mag, np.abs(ref)) < 1e-6
+    # the natural-order pair step (A/B alternative of the paired-column form that n_fft <= 1024 runs by default)
+    out_n, _ = E.emu_stft(x, n_fft, win, hop, w, pads[0], pads[1], E.MODE_COMPLEX, fmt, fmt, TF=16, n_warps=4, fb_mma=4)
+    assert nerr(out_n, ref) < 1e-6
+    assert nerr(out_n, out) < 3e-7
 
 
 @pytest.mark.parametrize('dbuf,bulk', [(0, 1), (0, 0)])
@@ -65,7 +69,8 @@ def test_emu_mel_and_db(n_fft, hop, n_mels, sr, TF, nw, fmt):
     # two-level walk over band descriptors: the same sums in the same order -> bit-identical
     out2, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw, fb_mma=2)
     assert np.array_equal(out, out2)
-    # paired-column pair step (kb_col_dftq_pair_mag): same magnitudes up to the rounding of the twiddles of bins >= P/2
+    # natural-order pair step (the A/B alternative of the default paired-column form): same magnitudes up to the rounding
+    # of the twiddles of bins >= P/2
     out3, _ = E.emu_stft(x, n_fft, n_fft, hop, w, False, False, E.MODE_FB, fmt, fmt, fb=fb, TF=TF, n_warps=nw, fb_mma=4)
     assert nerr(out3, ref) < 1e-6
     assert nerr(out3, out) < 3e-7
