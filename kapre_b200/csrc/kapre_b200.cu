@@ -1015,8 +1015,14 @@ int kapre_stft_forward(const kapre_stft_plan* plan, const float* x_dev, const ka
                 q.G = G;
                 q.pad1 = (q.n_pass > 0 && q.radix[0] % 2 == 0) ? 1 : 0;
                 q.FRT = FRT;
-                q.TF = FRT > 0 ? FRT : 4 * (NW / G);
                 if (fbmode) { q.bands = fb->bands; q.fbw = fb->w; q.n_bands = fb->n_bands; }
+                kb_mr_finish(q);
+                // frames per group and tile: 16 amortises the per-tile bookkeeping (two divisions, 64-bit bases) unless the
+                // batch is small -- keep at least ~8 tiles per resident CTA for the tail
+                int fpg = 16;
+                while (fpg > 4 && (long long)B * C * ((T + fpg * (NW / G) - 1) / (fpg * (NW / G))) < 8LL * plan->dev.sm_count * bps)
+                    fpg >>= 1;
+                q.TF = FRT > 0 ? FRT : fpg * (NW / G);
                 if (dbmode) {
                     q.amin = db->amin; q.db_mul = db_mul; q.db_sub = db_sub; q.item_max = (unsigned int*)workspace_dev;
                     q.db_ftz = (db->amin >= 1.17549435e-38f) ? 1 : 0;

@@ -18,8 +18,19 @@
 // sizes with a prime factor > 5).
 #pragma once
 #include "aux_core.cuh"
+#include "stft_mc_core.cuh"   // kb_magic / kb_fdiv
 
 #define KB_MR_MAX_PASS 12
+
+// one Stockham pass: radix r after radices of product ns
+struct alignas(16) KbMrPass {
+    int r, ns;
+    int tstep;        // P / (ns r): exp(-2 pi i t k / (ns r)) = tw_s[t k tstep]
+    int kinc;         // (32 G) mod ns: step of k = j mod ns when j advances by the group size
+    unsigned magic;   // kb_magic(ns)
+    int nb;           // P / r butterflies
+    int pad0, pad1;
+};
 
 struct KbMrParams {
     KbDftParams d;            // tensors, sizes, window (w[0, win_eff)), tw = exp(-2 pi i r / n_fft), mode, n_warps
@@ -30,6 +41,12 @@ struct KbMrParams {
     int TF;                   // frames per tile (= frames per group per tile * n_warps / G)
     int G;                    // warps per frame
     int pad1;                 // the buffer between pass 0 and pass 1 is indexed i + (i >> 4)
+    // constants the host precomputes (kb_mr_finish) so that the kernel's loops contain no division and do not
+    // re-derive the shared-memory layout
+    KbMrPass pass[KB_MR_MAX_PASS];
+    int bufsz;                    // kb_mr_bufsz(P)
+    int off_buf, off_mag, off_outs, Mp;   // kb_mr_smem_layout
+    int sk1;                      // output bins are contiguous (o_sk == 1)
     // fused tail (modes KB_OUT_MAG_DB, KB_OUT_FB, KB_OUT_FB_DB; kapre/time_frequency.py:535-548, kapre/backend.py:186-192)
     int FRT;                  // filterbank modes: frames per tile (32 / 16 / 8) = columns of the magnitude tile; else 0
     const KbBand* bands;
@@ -93,6 +110,27 @@ static inline int kb_mr_pick(int P, int smem_optin, int smem_sm, int want, int* 
     return best;
 }
 
+// host-side constants of a launch; call once G, n_warps, FRT and the tensors are set
+static inline void kb_mr_finish(KbMrParams& q) {
+    int Ns = 1;
+    const int GS = 32 * q.G;
+    for (int ps = 0; ps < q.n_pass; ++ps) {
+        KbMrPass& w = q.pass[ps];
+        w.r = q.radix[ps];
+        w.ns = Ns;
+        w.tstep = q.P / (Ns * w.r);
+        w.kinc = GS % Ns;
+        w.magic = kb_magic((unsigned)Ns);
+        w.nb = q.P / w.r;
+        w.pad0 = w.pad1 = 0;
+        Ns *= w.r;
+    }
+    q.bufsz = kb_mr_bufsz(q.P);
+    const KbMrSmem L = kb_mr_smem_layout(q.P, q.d.n_warps / q.G, q.d.n_fft / 2 + 1, q.n_bands, q.FRT);
+    q.off_buf = L.buf; q.off_mag = L.mag; q.off_outs = L.outs; q.Mp = L.Mp;
+    q.sk1 = q.d.o_sk == 1 ? 1 : 0;
+}
+
 KB_HD cpx kb_mul_mi(cpx a) { return cmake(a.im, -a.re); }   // a * (-i)
 
 // forward DFTs of size r on v[0..r)
@@ -132,47 +170,61 @@ KB_HD void kb_dft_r5(cpx* v) {
     v[2] = cadd(r2, q2); v[3] = csub(r2, q2);
 }
 
-// one Stockham pass of radix RDX for thread gl of a group of GS threads (butterflies j = gl, gl + GS, ...)
+// one Stockham pass of radix RDX for thread gl of a group of GS threads (butterflies j = gl, gl + GS, ...);
+// k = gl mod Ns on entry, stepped with j
 template <int RDX, bool PIN, bool POUT>
-KB_FN void kb_mr_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw_s, int P, int Ns, int gl, int GS) {
-    const int nb = P / RDX;                 // butterflies
-    const int tstep = P / (Ns * RDX);       // exp(-2 pi i t k / (Ns r)) = tw_s[t k tstep]
-    int k = gl % Ns;                        // j mod Ns, stepped with j (two divisions per pass, not per butterfly)
-    const int kinc = GS % Ns;
-    for (int j = gl; j < nb; j += GS, k = (k + kinc >= Ns) ? k + kinc - Ns : k + kinc) {
+KB_FN void kb_mr_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw_s, int nb, int Ns,
+                      int tstep, int kinc, int k, int gl, int GS) {
+    for (int j = gl; j < nb; j += GS) {
         cpx v[RDX];
+        if (PIN) {
+            int i = j;
 #pragma unroll
-        for (int t = 0; t < RDX; ++t) { const int i = j + t * nb; v[t] = in[PIN ? i + (i >> 4) : i]; }
+            for (int t = 0; t < RDX; ++t) { v[t] = in[i + (i >> 4)]; i += nb; }
+        } else {
+            const cpx* pi = in + j;
+#pragma unroll
+            for (int t = 0; t < RDX; ++t) { v[t] = *pi; pi += nb; }
+        }
         if (Ns > 1) {
             const int kt = k * tstep;
-            int ti = kt;
+            const cpx* tp = tw_s + kt;
 #pragma unroll
-            for (int t = 1; t < RDX; ++t) { v[t] = cmul(v[t], tw_s[ti]); ti += kt; }
+            for (int t = 1; t < RDX; ++t) { v[t] = cmul(v[t], *tp); tp += kt; }
         }
         if (RDX == 2) kb_dft_r2(v);
         else if (RDX == 3) kb_dft_r3(v);
         else if (RDX == 4) kb_dft_r4(v);
         else if (RDX == 8) kb_dft_r8(v);
         else kb_dft_r5(v);
-        const int j0 = (j - k) * RDX + k;
+        if (POUT) {
+            int i = (j - k) * RDX + k;
 #pragma unroll
-        for (int t = 0; t < RDX; ++t) { const int i = j0 + t * Ns; out[POUT ? i + (i >> 4) : i] = v[t]; }
+            for (int t = 0; t < RDX; ++t) { out[i + (i >> 4)] = v[t]; i += Ns; }
+        } else {
+            cpx* po = out + ((j - k) * RDX + k);
+#pragma unroll
+            for (int t = 0; t < RDX; ++t) { *po = v[t]; po += Ns; }
+        }
+        k += kinc;
+        if (k >= Ns) k -= Ns;
     }
 }
 template <bool PIN, bool POUT>
-KB_FN void kb_mr_pass_r(int r, const cpx* in, cpx* out, const cpx* tw_s, int P, int Ns, int gl, int GS) {
-    if (r == 8) kb_mr_pass<8, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
-    else if (r == 4) kb_mr_pass<4, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
-    else if (r == 2) kb_mr_pass<2, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
-    else if (r == 3) kb_mr_pass<3, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
-    else kb_mr_pass<5, PIN, POUT>(in, out, tw_s, P, Ns, gl, GS);
+KB_FN void kb_mr_pass_r(int r, const cpx* in, cpx* out, const cpx* tw_s, int nb, int Ns, int tstep, int kinc, int k, int gl,
+                        int GS) {
+    if (r == 8) kb_mr_pass<8, PIN, POUT>(in, out, tw_s, nb, Ns, tstep, kinc, k, gl, GS);
+    else if (r == 4) kb_mr_pass<4, PIN, POUT>(in, out, tw_s, nb, Ns, tstep, kinc, k, gl, GS);
+    else if (r == 2) kb_mr_pass<2, PIN, POUT>(in, out, tw_s, nb, Ns, tstep, kinc, k, gl, GS);
+    else if (r == 3) kb_mr_pass<3, PIN, POUT>(in, out, tw_s, nb, Ns, tstep, kinc, k, gl, GS);
+    else kb_mr_pass<5, PIN, POUT>(in, out, tw_s, nb, Ns, tstep, kinc, k, gl, GS);
 }
 
 // synchronisation of one frame group: a warp barrier when G == 1, else a named barrier (ids 1 .. 15) over its G warps
 #if defined(KB_HOST_EMU)
 #define KB_MR_SYNC
 #else
-#define KB_MR_SYNC do { if (q.G == 1) __syncwarp(); else asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)(threadIdx.x >> 5) / q.G), "r"(q.G * 32) : "memory"); } while (0)
+#define KB_MR_SYNC do { if (q.G == 1) __syncwarp(); else asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)(threadIdx.x >> gsh)), "r"(GS) : "memory"); } while (0)
 #endif
 
 template <int FRT>
@@ -189,13 +241,16 @@ __device__ __forceinline__ void kb_mr_cta_t(const KbMrParams& q, char* smem, int
     (void)kb_nt;
     const int N = p.n_fft, We = p.win_eff, F = N / 2 + 1, P = q.P;
     const int G = q.G, GS = G * 32, NG = NW / G;
-    const KbMrSmem L = kb_mr_smem_layout(P, NG, F, q.n_bands, FRT);
-    cpx* tw_s = reinterpret_cast<cpx*>(smem + L.tw);
-    float* mag_s = reinterpret_cast<float*>(smem + L.mag);
-    float* out_s = reinterpret_cast<float*>(smem + L.outs);
+    const int gsh = 5 + kb_ilog2(G);         // G is a power of two: group = tid >> gsh, thread in group = tid & (GS - 1)
+    struct { int buf, Mp; } L;                 // kb_mr_smem_layout, precomputed by kb_mr_finish
+    L.buf = q.off_buf; L.Mp = q.Mp;
+    cpx* tw_s = reinterpret_cast<cpx*>(smem);
+    float* mag_s = reinterpret_cast<float*>(smem + q.off_mag);
+    float* out_s = reinterpret_cast<float*>(smem + q.off_outs);
+    (void)NG;
     const bool dbmode = p.mode == KB_OUT_MAG_DB || p.mode == KB_OUT_FB_DB;
     (void)mag_s; (void)out_s;
-    const int bufsz = kb_mr_bufsz(P);
+    const int bufsz = q.bufsz;
     const int n_tiles_t = (p.T + q.TF - 1) / q.TF;
     const int n_tiles = p.B * p.C * n_tiles_t;
     const int fpw = q.TF / NG;               // frames per group and tile
@@ -224,7 +279,7 @@ __device__ __forceinline__ void kb_mr_cta_t(const KbMrParams& q, char* smem, int
             // every step below is private to one group of G warps (its own two buffers): group-level synchronisation only
             KB_PHASE_BEGIN
                 (void)R;
-                const int grp = tid / GS, gl = tid - grp * GS;
+                const int grp = tid >> gsh, gl = tid & (GS - 1);
                 const int t = tt * q.TF + grp * fpw + fi;
                 cpx* A = reinterpret_cast<cpx*>(smem + L.buf + (grp * 2) * bufsz);
                 if (t < p.T) {
@@ -232,16 +287,28 @@ __device__ __forceinline__ void kb_mr_cta_t(const KbMrParams& q, char* smem, int
                     const bool interior = s0 >= 0 && s0 + N <= p.L && We == N && p.x_sl == 1 &&
                                           (((reinterpret_cast<uintptr_t>(xsig) >> 2) + (uintptr_t)s0) & 1u) == 0;
                     if (q.half && interior) {
-                        // whole frame inside the signal, 8-byte aligned: one vector load of (x[2n], x[2n+1]) and of the window pair
+                        // whole frame inside the signal, 8-byte aligned: vector loads of (x[2n], x[2n+1]) and of the window
+                        // pair, four trips' loads in flight before the first multiply
                         const float2* xp = reinterpret_cast<const float2*>(xsig + s0);
                         const float2* wp = reinterpret_cast<const float2*>(p.w);
-                        for (int n = gl; n < P; n += GS) {
+                        for (int n0 = gl; n0 < P; n0 += 4 * GS) {
+                            float2 xv[4], wv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int n = n0 + u * GS;
+                                if (n < P) {
 #if defined(KB_HOST_EMU)
-                            const float2 xv = xp[n], wv = wp[n];
+                                    xv[u] = xp[n]; wv[u] = wp[n];
 #else
-                            const float2 xv = __ldg(xp + n), wv = __ldg(wp + n);
+                                    xv[u] = __ldg(xp + n); wv[u] = __ldg(wp + n);
 #endif
-                            A[n] = cmake(xv.x * wv.x, xv.y * wv.y);
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int n = n0 + u * GS;
+                                if (n < P) A[n] = cmake(xv[u].x * wv[u].x, xv[u].y * wv[u].y);
+                            }
                         }
                     } else if (q.half) {
                         for (int n = gl; n < P; n += GS) {
@@ -264,28 +331,28 @@ __device__ __forceinline__ void kb_mr_cta_t(const KbMrParams& q, char* smem, int
                 }
             KB_PHASE_END
             KB_MR_SYNC;
-            int Ns = 1;
             for (int ps = 0; ps < q.n_pass; ++ps) {
-                const int r = q.radix[ps];
+                const KbMrPass w = q.pass[ps];
+                const int r = w.r, Ns = w.ns;
                 KB_PHASE_BEGIN
                     (void)R;
-                    const int grp = tid / GS, gl = tid - grp * GS;
+                    const int grp = tid >> gsh, gl = tid & (GS - 1);
                     const int t = tt * q.TF + grp * fpw + fi;
                     cpx* b0 = reinterpret_cast<cpx*>(smem + L.buf + (grp * 2) * bufsz);
                     cpx* b1 = reinterpret_cast<cpx*>(smem + L.buf + (grp * 2 + 1) * bufsz);
                     const cpx* in = (ps & 1) ? b1 : b0;
                     cpx* out = (ps & 1) ? b0 : b1;
                     if (t < p.T) {
-                        if (q.pad1 && ps == 0) kb_mr_pass_r<false, true>(r, in, out, tw_s, P, Ns, gl, GS);
-                        else if (q.pad1 && ps == 1) kb_mr_pass_r<true, false>(r, in, out, tw_s, P, Ns, gl, GS);
-                        else kb_mr_pass_r<false, false>(r, in, out, tw_s, P, Ns, gl, GS);
+                        const int k = gl - Ns * kb_fdiv(gl, Ns, w.magic);   // gl mod Ns
+                        if (ps > 1 || !q.pad1) kb_mr_pass_r<false, false>(r, in, out, tw_s, w.nb, Ns, w.tstep, w.kinc, k, gl, GS);
+                        else if (ps == 0) kb_mr_pass_r<false, true>(r, in, out, tw_s, w.nb, Ns, w.tstep, w.kinc, k, gl, GS);
+                        else kb_mr_pass_r<true, false>(r, in, out, tw_s, w.nb, Ns, w.tstep, w.kinc, k, gl, GS);
                     }
                 KB_PHASE_END
                 KB_MR_SYNC;
-                Ns *= r;
             }
             KB_PHASE_BEGIN
-                const int grp = tid / GS, gl = tid - grp * GS;
+                const int grp = tid >> gsh, gl = tid & (GS - 1);
                 const int t = tt * q.TF + grp * fpw + fi;
                 const cpx* Z = reinterpret_cast<const cpx*>(smem + L.buf + (grp * 2 + (q.n_pass & 1)) * bufsz);
                 const bool zp = q.pad1 && q.n_pass == 1;   // a single pass leaves its (padded) output as the spectrum
@@ -296,32 +363,49 @@ __device__ __forceinline__ void kb_mr_cta_t(const KbMrParams& q, char* smem, int
                     float* mcol = mag_s + (grp * fpw + fi);          // FRT > 0: this frame's column of the magnitude tile
                     (void)mcol;
                     float rmax = R.runmax;
-                    const int kend = q.half ? P + 1 : F;
-                    for (int k = gl; k < kend; k += GS) {
-                        cpx X;
+                    const long long sk = p.o_sk;
+                    // all bins of the frame through emit(k, X[k]); the output form is picked once per frame, not per bin
+                    auto bins = [&](auto emit) {
                         if (q.half) {
-                            // X[k] = (Z[k] + conj Z[P-k]) / 2 - i/2 exp(-2 pi i k / N) (Z[k] - conj Z[P-k]),  k = 0 .. P
-                            const int ia = k == P ? 0 : k, ib = (k == 0 || k == P) ? 0 : P - k;
-                            const cpx a = Z[zp ? ia + (ia >> 4) : ia];
-                            const cpx bq = Z[zp ? ib + (ib >> 4) : ib];
-                            const cpx e = cadd_conj(a, bq), dd = csub_conj(a, bq);
-                            float2 w2;
-                            if (k == P) w2 = make_float2(-1.0f, 0.0f);
-                            else { w2.x = kb_ldg(reinterpret_cast<const float*>(p.tw + k)); w2.y = kb_ldg(reinterpret_cast<const float*>(p.tw + k) + 1); }
-                            const cpx tq = cmul(cmake(dd.im, -dd.re), cmake(w2.x, w2.y));
-                            X = cscale(cadd(e, tq), 0.5f);
+                            // X[k]   = (Z[k] + conj Z[P-k]) / 2 - i/2 exp(-2 pi i k / N) (Z[k] - conj Z[P-k]),  k = 0 .. P/2,  and from
+                            // the same operands its mirror image X[P-k] = conj((Z[k] + conj Z[P-k]) / 2 + i/2 exp(..) (Z[k] - conj Z[P-k]))
+                            const int hk = P >> 1;
+                            for (int k = gl; k <= hk; k += GS) {
+                                const int km = P - k, ib = k == 0 ? 0 : km;
+                                const cpx a = Z[zp ? k + (k >> 4) : k];
+                                const cpx bq = Z[zp ? ib + (ib >> 4) : ib];
+                                const cpx e = cadd_conj(a, bq), dd = csub_conj(a, bq);
+#if defined(KB_HOST_EMU)
+                                const float2 w2 = p.tw[k];
+#else
+                                const float2 w2 = __ldg(p.tw + k);
+#endif
+                                const cpx tq = cmul(cmake(dd.im, -dd.re), cmake(w2.x, w2.y));
+                                emit(k, cscale(cadd(e, tq), 0.5f));
+                                if (km != k) {
+                                    const cpx xm = cscale(csub(e, tq), 0.5f);
+                                    emit(km, cmake(xm.re, -xm.im));
+                                }
+                            }
                         } else {
-                            X = Z[zp ? k + (k >> 4) : k];
+                            for (int k = gl; k < F; k += GS) emit(k, Z[zp ? k + (k >> 4) : k]);
                         }
-                        if (p.mode == KB_OUT_COMPLEX) { oc[(long long)k * p.o_sk] = make_float2(X.re, X.im); continue; }
-                        float v = kb_sqrt(cnorm(X));
-                        if (FRT > 0) { mcol[k * RS] = v; continue; }
-                        if (p.mode == KB_OUT_MAG_DB) {
-                            v = kb_floor_keepnan(v, q.amin);
-                            rmax = kb_max_keepnan(rmax, v);
-                            v = q.db_mul * (q.db_ftz ? kb_lg2_ftz(v) : kb_log2(v)) - q.db_sub;
-                        }
-                        orl[(long long)k * p.o_sk] = v;
+                    };
+                    auto db = [&](float v) {
+                        v = kb_floor_keepnan(v, q.amin);
+                        rmax = kb_max_keepnan(rmax, v);
+                        return q.db_mul * (q.db_ftz ? kb_lg2_ftz(v) : kb_log2(v)) - q.db_sub;
+                    };
+                    if (FRT > 0) bins([&](int k, cpx X) { mcol[k * RS] = kb_sqrt(cnorm(X)); });
+                    else if (p.mode == KB_OUT_COMPLEX) {
+                        if (q.sk1) bins([&](int k, cpx X) { oc[k] = make_float2(X.re, X.im); });
+                        else bins([&](int k, cpx X) { oc[k * sk] = make_float2(X.re, X.im); });
+                    } else if (p.mode == KB_OUT_MAG_DB) {
+                        if (q.sk1) bins([&](int k, cpx X) { orl[k] = db(kb_sqrt(cnorm(X))); });
+                        else bins([&](int k, cpx X) { orl[k * sk] = db(kb_sqrt(cnorm(X))); });
+                    } else {
+                        if (q.sk1) bins([&](int k, cpx X) { orl[k] = kb_sqrt(cnorm(X)); });
+                        else bins([&](int k, cpx X) { orl[k * sk] = kb_sqrt(cnorm(X)); });
                     }
                     R.runmax = rmax;
                 }

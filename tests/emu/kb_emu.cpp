@@ -334,6 +334,7 @@ int kb_emu_mr(const float* x, long long x_sb, long long x_sc, long long x_sl, in
     }
     q.amin = amin; q.db_mul = db_mul; q.db_sub = db_sub; q.item_max = item_max;
     q.db_ftz = (amin >= 1.17549435e-38f) ? 1 : 0;
+    kb_mr_finish(q);
     const KbMrSmem L_ = kb_mr_smem_layout(q.P, n_warps / group, n_fft / 2 + 1, q.n_bands, q.FRT);
     std::vector<char> smem(L_.total + 64);
     for (int cta = 0; cta < n_cta; ++cta) {
