@@ -49,6 +49,40 @@ def test_stft_complex_vs_oracle(K, n_fft, win, hop, fmt, pad):
     assert nerr(got, ref) < 2e-6  # fp32 FFT vs float64 truth, normalised max-abs
 
 
+@pytest.mark.parametrize('mode', ['complex', 'magnitude', 'mel_db'])
+def test_pair_step_forms_agree(K, monkeypatch, mode):
+    """n_fft 1024 carries both forms of the real-FFT pair step (paired columns: the default; natural order:
+    KAPRE_B200_PAIRED=0, the A/B alternative).  Both against the oracle and against each other."""
+    from kapre_b200 import _native
+    rng = np.random.default_rng(7)
+    x = wave(rng, 3, 1, 22050, 'channels_last')
+    xt = torch.from_numpy(x).cuda()
+    if mode == 'complex':
+        layer = K.STFT(n_fft=1024, hop_length=256, pad_begin=True)
+        ref = O.stft_layer(x, 1024, 1024, 256, None, True, False, 'channels_last', 'channels_last')
+    elif mode == 'magnitude':
+        layer = K.get_stft_magnitude_layer(n_fft=1024, hop_length=256)
+        ref = O.stft_magnitude_layer(x, 1024, None, 256, input_data_format='channels_last', output_data_format='channels_last')
+    else:
+        layer = K.get_melspectrogram_layer(n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128, return_decibel=True,
+                                           db_dynamic_range=1e9)
+        ref = O.melspectrogram_layer(x, n_fft=1024, hop_length=256, sample_rate=22050, n_mels=128, return_decibel=True,
+                                     db_dynamic_range=1e9)
+    outs = {}
+    for paired in ('1', '0'):
+        monkeypatch.setenv('KAPRE_B200_PAIRED', paired)
+        y = layer(xt).cpu().numpy()
+        info = _native.last_launch_info()
+        assert info.endswith('v0' if paired == '1' else 'v2'), info
+        outs[paired] = y
+    if mode == 'mel_db':
+        assert np.abs(outs['1'] - ref).max() < 2e-3 and np.abs(outs['0'] - ref).max() < 2e-3      # dB
+        assert np.abs(outs['1'] - outs['0']).max() < 2e-3
+    else:
+        assert nerr(outs['1'], ref) < 2e-6 and nerr(outs['0'], ref) < 2e-6
+        assert nerr(outs['1'], outs['0']) < 5e-7
+
+
 @pytest.mark.parametrize('ifmt', ['channels_first', 'channels_last'])
 @pytest.mark.parametrize('ofmt', ['channels_first', 'channels_last'])
 def test_stft_mixed_formats(K, ifmt, ofmt):
