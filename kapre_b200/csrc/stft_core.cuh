@@ -87,7 +87,7 @@ struct KbThreadRegs {
 static inline float kb_sqrt(float v) { return std::sqrt(v); }
 static inline float kb_log2(float v) { return std::log2(v); }
 static inline float kb_lg2_ftz(float v) { return std::log2(v); }
-static inline float kb_atan2(float y, float x) { return std::atan2(y, x); }
+static inline float kb_fdividef(float a, float b) { return a / b; }
 static inline float kb_ldg(const float* p) { return *p; }
 static inline void kb_atomic_max_u32(unsigned int* p, unsigned int v) { if (v > *p) *p = v; }
 static inline unsigned int kb_f2u(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
@@ -104,7 +104,7 @@ static inline void kb_bar_wait(KbBar*, unsigned) {}
 KB_D float kb_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 KB_D float kb_log2(float v) { return __log2f(v); }
 KB_D float kb_lg2_ftz(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
-KB_D float kb_atan2(float y, float x) { return atan2f(y, x); }
+KB_D float kb_fdividef(float a, float b) { return __fdividef(a, b); }
 KB_D float kb_ldg(const float* p) { return __ldg(p); }
 KB_D void kb_atomic_max_u32(unsigned int* p, unsigned int v) { atomicMax(p, v); }
 KB_D unsigned int kb_f2u(float f) { return __float_as_uint(f); }
@@ -133,6 +133,35 @@ KB_D void kb_bar_wait(KbBar* bar, unsigned parity) {
         ::"r"(b), "r"(parity) : "memory");
 }
 #endif
+
+// atan2 for the Phase outputs (tf.math.angle, kapre/time_frequency.py:402): octant reduction to t = min / max in [0, 1],
+// atan(t) = t + t s q(s), s = t^2, q a degree-7 minimax fit (weighted least squares on Chebyshev nodes): max error 2.8e-7 rad
+// over random float32 arguments, the same as a correctly rounded float32 atan2 within 1 ulp of pi -- and ~20 instructions
+// instead of the ~45 of atan2f (the magnitude + phase mode spends most of its time here).  Signed zeros and the quadrants
+// follow atan2f; atan2(0, 0) = 0.
+#if defined(KB_HOST_EMU)
+static inline float kb_atan2(float y, float x)
+#else
+KB_D float kb_atan2(float y, float x)
+#endif
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mx == 0.0f ? 0.0f : kb_fdividef(mn, mx);
+    const float s = t * t;
+    float r = 0.0026222908826366536f;
+    r = fmaf(r, s, -0.015132737140170525f);
+    r = fmaf(r, s, 0.04112221452660872f);
+    r = fmaf(r, s, -0.07366738638336225f);
+    r = fmaf(r, s, 0.10573948441726781f);
+    r = fmaf(r, s, -0.14185979604290994f);
+    r = fmaf(r, s, 0.199903971231639f);
+    r = fmaf(r, s, -0.3333298707427664f);
+    r = fmaf(r * s, t, t);
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (kb_f2u(x) >> 31) r = 3.14159265358979324f - r;   // incl. x = -0: atan2(+-0, -0) = +-pi
+    return copysignf(r, y);
+}
 
 // ---- tensor-core filterbank primitives ------------------------------------------------------
 // A-fragment element (frame f, bin k) of the tile's magnitudes: region of warp f / FPW, [bin][frame-in-warp].
@@ -650,9 +679,10 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
     // Pair step: the paired-column form (kb_col_dftq_pair) whenever a lane owns two or more columns (n_fft <= 1024), except
     // where its output pattern costs more than the shared-memory trips it saves: a lane then writes bins q + 32 i, i.e. runs
     // of Q consecutive bins per frame instead of 32 -- measured on B256 x 5 s (profiles/r2_small_experiments.md): complex
-    // output n_fft 512 / 256 +31 % / +68 % (store-bound modes), magnitude + phase n_fft 256 +5 %, everything else -1 ... -11 %.
+    // output n_fft 512 / 256 +31 % / +68 % (store-bound modes), magnitude + phase (two output planes) n_fft 512 / 256 +36 % /
+    // +5 % once the phase is the fast kb_atan2, everything else -1 ... -11 %.
     // FBMMA bit 1 selects the other form (the A/B alternative).
-    constexpr bool prefer_natural = (MODE == KB_OUT_COMPLEX && Q < 16) || (MODE == KB_OUT_MAG_PHASE && Q == 4);
+    constexpr bool prefer_natural = (MODE == KB_OUT_COMPLEX && Q < 16) || (MODE == KB_OUT_MAG_PHASE && Q <= 8);
     constexpr bool paired = FPW >= 2 && !fbmma && (((FBMMA & 2) != 0) == prefer_natural);
     const KbStftSmem L = kb_stft_smem_layout(Q, N, H, TF, NW, MODE, p.n_bands, fbmma ? p.n_msteps : p.n_chunks,
                                              fbmma ? 1 : 0);
