@@ -388,4 +388,9 @@ int kb_emu_fb(const float* x, long long x_sb, long long x_sc, long long x_st, lo
     return 0;
 }
 
+// kb_atan2 (the Phase outputs' polynomial atan2) on arrays, for the accuracy test
+void kb_emu_atan2(const float* y, const float* x, float* out, long long n) {
+    for (long long i = 0; i < n; ++i) out[i] = kb_atan2(y[i], x[i]);
+}
+
 }  // extern "C"

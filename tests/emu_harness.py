@@ -261,3 +261,13 @@ def emu_fb(x, fb, fmt, n_cta=3, R=32):
                        LL(osc), LL(ost), LL(osk), n_cta, R)
     assert rc == 0
     return out
+
+
+def emu_atan2(y, x):
+    """kb_atan2 of kapre_b200/csrc/stft_core.cuh (host build of the same source) on float32 arrays."""
+    lib = load()
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    lib.kb_emu_atan2(_fp(y), _fp(x), _fp(out), ctypes.c_longlong(y.size))
+    return out

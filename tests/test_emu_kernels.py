@@ -381,3 +381,20 @@ def test_emu_standalone_filterbank(fmt, F, M, kind):
     assert nerr(out, ref) < 2e-6
     for R in (16, 4, 1):          # shorter tiles: what long spectra (n_fft >= 4096) fall back to
         assert nerr(E.emu_fb(x, fb, fmt, n_cta=2, R=R), ref) < 2e-6
+
+
+def test_emu_atan2_accuracy_and_special_values():
+    """kb_atan2 (octant reduction + degree-7 minimax polynomial) against float64 arctan2: as accurate as a float32 atan2
+    can be near pi (1 ulp = 2.4e-7), quadrants and signed zeros as atan2f (tf.math.angle, kapre/time_frequency.py:402)."""
+    rng = np.random.default_rng(3)
+    n = 1_000_000
+    x = (rng.normal(size=n) * 10.0 ** rng.integers(-6, 6, n)).astype(np.float32)
+    y = (rng.normal(size=n) * 10.0 ** rng.integers(-6, 6, n)).astype(np.float32)
+    y[: n // 4] = x[: n // 4] * (1 + 0.3 * rng.normal(size=n // 4)).astype(np.float32)      # around the octant boundaries
+    got = E.emu_atan2(y, x).astype(np.float64)
+    ref = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    assert np.abs(got - ref).max() < 4e-7
+    ys = np.array([0.0, 0.0, -0.0, 1.0, -1.0, 0.0, -0.0, 0.0, 3.0, -3.0], np.float32)
+    xs = np.array([1.0, -1.0, -1.0, 0.0, 0.0, 0.0, 0.0, -0.0, -0.0, 0.0], np.float32)
+    np.testing.assert_allclose(E.emu_atan2(ys, xs), np.arctan2(ys, xs), atol=3e-7)
+    assert np.array_equal(np.signbit(E.emu_atan2(ys, xs)), np.signbit(np.arctan2(ys, xs)))
