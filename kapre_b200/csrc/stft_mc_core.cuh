@@ -484,6 +484,7 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
     constexpr int FPW = 32 / Q;
     constexpr int ZSTR = P + Q;
     constexpr bool dbmode = (MODE == KB_OUT_FB_DB);
+    constexpr bool paired = FPW >= 2;          // paired-column pair step (stft_core.cuh) whenever a lane owns two or more columns
     const int NW = p.n_warps;
     const int kb_nt = NW * 32;
     (void)kb_nt;
@@ -516,7 +517,7 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
         (void)R;
         if (p.mc_wh) { for (int i = tid; i < N; i += kb_nt) wh_s[i] = p.wh[i]; }
         for (int i = tid; i < Q * 33; i += kb_nt) { float2 t = p.twp[i]; twp_s[i] = cmake(t.x, t.y); }
-        for (int i = tid; i < P / 2; i += kb_nt) { float2 t = p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
+        for (int i = tid; i < P / 2; i += kb_nt) { float2 t = paired ? p.twn2[i] : p.twn[i]; twn_s[i] = cmake(t.x, t.y); }
         if (p.cosw) { for (int i = tid; i < Q; i += kb_nt) cwq_s[i] = p.cwq[i]; }
         for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
         for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.cg[i];
@@ -551,10 +552,35 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
             const int col = warp * FPW + g;
             if (col < NCOL) {
                 const int fl = kb_fdiv(col, C, p.mc_magic_c), ch = col - fl * C;
-                kb_col_window_dft32<Q>(R, smp + ch * spanp + fl * H, wh_s, cwq_s, p.cw_a0, twp_s, ex_s + warp * EXS, g, q,
-                                       wmode);
+                kb_col_window_dft32<Q, paired>(R, smp + ch * spanp + fl * H, wh_s, cwq_s, p.cw_a0, twp_s, ex_s + warp * EXS, g, q,
+                                               wmode);
             }
         KB_PHASE_END
+        if constexpr (paired) {
+        // ---- phases 2-4, paired-column form (stft_core.cuh: kb_col_gather_paired / kb_col_dftq_pair_mag) ----
+        KB_SYNC_WARP;
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            const int g = lane / Q, q = lane % Q;
+            if (warp * FPW + g < NCOL) {
+                kb_col_gather_paired<Q>(R, ex_s + warp * EXS, g, q);
+            } else {   // column past the tile: its magnitudes must read as zeros in the filterbank phase
+#pragma unroll
+                for (int i = 0; i < 32; ++i) R.v[i] = cmake(0.0f, 0.0f);
+            }
+        KB_PHASE_END
+        KB_SYNC_WARP;
+        KB_PHASE_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            const int g = lane / Q, q = lane % Q;
+            float* mw = reinterpret_cast<float*>(ex_s + warp * EXS);
+            kb_col_dftq_pair_mag<Q>(R, twn_s, mw, g, q);
+            if (lane < 3) {
+#pragma unroll
+                for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;   // pad bins
+            }
+        KB_PHASE_END
+        } else {
         KB_SYNC_WARP;
         // ---- phase 2: gather this lane's columns ----------------------------------------------
         KB_PHASE_BEGIN
@@ -635,6 +661,7 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
                 for (int gg = 0; gg < FPW; ++gg) mw[(P + 1 + lane) * FPW + gg] = 0.0f;   // pad bins
             }
         KB_PHASE_END
+        }
         KB_SYNC_CTA;      // all magnitudes visible; the sample planes are free
         if (has_next) {
             KB_PHASE_BEGIN
@@ -645,9 +672,9 @@ __device__ __forceinline__ void kb_stft_mcfb_cta(const KbStftParams& p, char* sm
         // ---- phase 5: filterbank (as in stft_core.cuh) ---------------------------------------------
         KB_PHASE_BEGIN
             (void)R;
-            const int warp = tid >> 5, lane = tid & 31;
-            const int w = lane % NW;
-            const int grp = warp * (32 / NW) + lane / NW;           // 0..31
+            // NW is a power of two (kb_pick_mcfb_cfg): lane group = tid / NW, lane within the group = tid % NW
+            const int w = tid & (NW - 1);
+            const int grp = tid >> kb_ilog2(NW);                    // 0..31
             const float* __restrict__ mw = reinterpret_cast<const float*>(ex_s + w * EXS);
             float* __restrict__ ocol = out_s + (w * FPW) * L.Mp;
             float a0[FPW], a1[FPW];

@@ -176,16 +176,17 @@ int kb_emu_stft_mc(const float* x, long long x_sb, long long x_sc, long long x_s
     const bool fbm = (mode == KB_OUT_FB || mode == KB_OUT_FB_DB);
     if (fbm && (!fb || TF * C > n_warps * (32 / Q) || (32 % n_warps) != 0)) return -2;   // kernel contract
     if (n_warps * (32 / Q) > 32) return -2;
-    std::vector<float> wh; std::vector<float2> twp, twn;
+    std::vector<float> wh; std::vector<float2> twp, twn, twn2;
     std::vector<kb_f4> cw; std::vector<kb_i2> cm; std::vector<int> cg;
     if (fbm) kb_make_fb_chunks(fb, n_freq, n_bands, 32, cw, cm, cg);
     kb_make_wh(window, win_length, n_fft, wh);
     kb_make_twp(Q, twp);
     kb_make_twn(n_fft, twn);
+    kb_make_twn2(n_fft, twn2);
     KbStftParams p{};
     p.x = x; p.x_sb = x_sb; p.x_sc = x_sc; p.x_sl = x_sl; p.B = B; p.C = C; p.L = L;
     p.n_fft = n_fft; p.hop = hop; p.T = T; p.pad_left = pad_left;
-    p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data();
+    p.wh = wh.data(); p.twp = twp.data(); p.twn = twn.data(); p.twn2 = twn2.data();
     std::vector<kb_f4> cwq;
     {
         double ca = 0.0, cb = 0.0;
