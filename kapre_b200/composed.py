@@ -9,6 +9,7 @@ launch (magnitudes never reach HBM); ``.layers`` remains usable one by one
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import numpy as np
@@ -25,6 +26,36 @@ __all__ = ['CapturedSequential', 'Sequential', 'StftMagPhase', 'get_stft_magnitu
 
 
 _streams = {}
+
+
+_copy_pool = None
+
+
+def _get_copy_pool():
+    global _copy_pool
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _copy_pool = ThreadPoolExecutor(8)
+    return _copy_pool
+
+
+def _host_copy(dst, src, min_bytes=1 << 20):
+    """Host-to-host copy of a contiguous tensor with a few memcpy threads (NumPy releases the GIL in ``copyto``).
+    ``Tensor.copy_`` between CPU tensors runs an OpenMP loop that was measured 50x slower than one memcpy on
+    CPU-restricted hosts (thread oversubscription); one thread moves ~12 GB/s, PCIe needs ~55 GB/s."""
+    d = dst.numpy().reshape(-1)
+    a = src.numpy().reshape(-1)
+    n = d.size
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        ncpu = os.cpu_count() or 1
+    k = max(1, min(8, ncpu, d.nbytes // min_bytes))
+    if k == 1:
+        np.copyto(d, a)
+        return
+    step = -(-n // k)
+    list(_get_copy_pool().map(lambda j: np.copyto(d[j * step:(j + 1) * step], a[j * step:(j + 1) * step]), range(k)))
 
 
 def _side_streams(dev):
@@ -140,11 +171,37 @@ class Sequential(Layer):
         s_in.wait_stream(s_comp)
         out_host = None
         keep = []
-        for i in range(0, B, chunk):
+        # Pageable input (what a kapre user's NumPy array is): a cudaMemcpy from pageable memory goes through the driver's own
+        # small staging buffer and blocks the host (~10 GB/s, nothing overlaps).  Instead every chunk is copied into its own
+        # page-locked staging buffer by a memcpy thread (all chunks at once: one thread moves ~12 GB/s, PCIe needs ~55), and
+        # the loop below only waits for chunk i's copy before it queues chunk i's DMA.  More than 16 chunks: a ring of three
+        # buffers, each reused only after the event recorded behind its DMA has completed.
+        n_chunks = -(-B // chunk)
+        stage = futs = None
+        if not xh.is_pinned():
+            stage = self._staging_ring((min(chunk, B),) + tuple(xh.shape[1:]), xh.dtype, n_chunks if n_chunks <= 16 else 3)
+            if n_chunks <= 16:
+                pool = _get_copy_pool()
+                futs = [pool.submit(_host_copy, stage[ci]['t'][:min(chunk, B - ci * chunk)], xh[ci * chunk:(ci + 1) * chunk], 1 << 62)
+                        for ci in range(n_chunks)]
+        for ci, i in enumerate(range(0, B, chunk)):
+            src = xh[i:i + chunk]
+            if stage is not None:
+                slot = stage[ci % len(stage)]
+                buf = slot['t'][:src.shape[0]]
+                if futs is not None:
+                    futs[ci].result()
+                else:
+                    if slot['ev'] is not None:
+                        slot['ev'].synchronize()
+                    _host_copy(buf, src)
+                src = buf
             with torch.cuda.stream(s_in):
-                xd = xh[i:i + chunk].to(dev, non_blocking=True)
+                xd = src.to(dev, non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
+            if stage is not None:
+                slot['ev'] = ev_in
             s_comp.wait_event(ev_in)
             xd.record_stream(s_comp)
             yd = self.call(xd)
@@ -159,6 +216,20 @@ class Sequential(Layer):
             keep.append((xd, yd))
         s_out.synchronize()
         return out_arr
+
+    def _staging_ring(self, shape, dtype, n=3):
+        """``n`` page-locked staging buffers for pageable host inputs.  ``cudaHostAlloc`` is slow (10-70 ms for a
+        cfg2-sized chunk), so the buffers are kept and only ever grow: a smaller chunk shape is a view of the same bytes."""
+        need = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        ring = self.__dict__.setdefault('_stage_ring', [])
+        for slot in ring:
+            if slot['raw'].numel() < need:
+                slot['raw'] = torch.empty((max(need, 1),), dtype=torch.uint8, pin_memory=True)
+        while len(ring) < n:
+            ring.append({'raw': torch.empty((max(need, 1),), dtype=torch.uint8, pin_memory=True), 'ev': None})
+        for slot in ring:
+            slot['t'] = slot['raw'][:need].view(dtype).view(shape)
+        return ring[:n]
 
     def capture(self, example):
         """Freeze this model for one input shape into a CUDA graph (``CapturedSequential``): replaying it
