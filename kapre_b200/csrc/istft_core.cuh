@@ -290,14 +290,25 @@ KB_FN void kb_istft2_prefetch(KbThreadRegs& R, const KbIstftParams& p, const flo
         t = t < 0 ? 0 : (t > p.T - 1 ? p.T - 1 : t);
         Xf[gg] = Xsig + (long long)t * p.x_st;
     }
+    if (p.x_sk == 1) {     // contiguous bins: one base per lane, compile-time offsets
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const int gg = e / HQ, i = e % HQ;
-        const int k = lane + 32 * i;
-        const float2 a = Xf[gg][(long long)k * p.x_sk];
-        const float2 b = Xf[gg][(long long)(P - k) * p.x_sk];
-        R.v[e] = cmake(a.x, a.y);
-        R.v[16 + e] = cmake(b.x, b.y);
+        for (int e = 0; e < 16; ++e) {
+            const int gg = e / HQ, i = e % HQ;
+            const float2 a = (Xf[gg] + lane)[32 * i];
+            const float2 b = (Xf[gg] + (P - lane))[-32 * i];
+            R.v[e] = cmake(a.x, a.y);
+            R.v[16 + e] = cmake(b.x, b.y);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int gg = e / HQ, i = e % HQ;
+            const int k = lane + 32 * i;
+            const float2 a = Xf[gg][(long long)k * p.x_sk];
+            const float2 b = Xf[gg][(long long)(P - k) * p.x_sk];
+            R.v[e] = cmake(a.x, a.y);
+            R.v[16 + e] = cmake(b.x, b.y);
+        }
     }
     {   // lane gg fetches the middle bin of the warp's frame gg (lanes >= FPW: a harmless duplicate of frame FPW - 1's)
         int t = tfr + warp * FPW + (lane < FPW ? lane : FPW - 1);
@@ -499,6 +510,7 @@ __device__ __forceinline__ void kb_istft2_cta(const KbIstftParams& p, char* smem
                     // f = h, h - 1, ... at offsets 4 i4, 4 i4 + H, ... (< win).  Frame f's samples start at float 2 ZSTR f
                     // of the exchange area (FPW ZSTR = 32 * 33: the warps' regions continue the stride).
                     const int H4 = H >> 2;
+                    const int Rw = (win + H - 1) / H, rem_w = win - (Rw - 1) * H;   // once per round, not per element
                     const float* exf = reinterpret_cast<const float*>(ex_s);
                     const int dstep = H - 2 * ZSTR;      // frame f -> f - 1 at the same output sample
                     float* yrow = ysig + s0;             // only dereferenced inside [u_lo, u_hi)
@@ -513,7 +525,11 @@ __device__ __forceinline__ void kb_istft2_cta(const KbIstftParams& p, char* smem
                             int off = (h - f_top) * H + i;
                             const float* fp = exf + f_top * (2 * ZSTR) + off;
                             int cnt = f_top - fv_lo + 1;                 // frames at or below f_top that exist ...
-                            if (cnt > 0 && off + (cnt - 1) * H >= win) cnt = off < win ? (win - off + H - 1) / H : 0;   // ... and reach sample u (rare path)
+                            // ... and reach sample u: offsets off, off + H, ... below win, i.e. ceil((win - off) / H) of them.  With
+                            // off = (h - f_top) H + i and win = (Rw - 1) H + rem that is (i < rem ? Rw : Rw - 1) - (h - f_top): no division
+                            int lim = (i < rem_w ? Rw : Rw - 1) - (h - f_top);
+                            if (lim < 0) lim = 0;
+                            if (cnt > lim) cnt = lim;
                             if (cnt == 4) {                              // the interior case at hop = win / 4: four independent loads
                                 const kb_f4 a0 = *reinterpret_cast<const kb_f4*>(fp);
                                 const kb_f4 a1 = *reinterpret_cast<const kb_f4*>(fp + dstep);
