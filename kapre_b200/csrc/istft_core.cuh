@@ -402,12 +402,15 @@ __device__ __forceinline__ void kb_istft2_cta(const KbIstftParams& p, char* smem
                     cpx bq = R.v[16 + e];
                     if (k == 0) { a.im = 0.0f; bq.im = 0.0f; }  // C2R ignores Im of DC / Nyquist
                     const cpx W = twn_s[k];
-                    const float Er = a.re + bq.re, Ei = a.im - bq.im;
-                    const float dr = a.re - bq.re, di = a.im + bq.im;
-                    const float Or = W.re * dr + W.im * di;
-                    const float Oi = W.re * di - W.im * dr;
-                    zf[k] = cmake(Er - Oi, -(Ei + Or));
-                    if (k != 0) zf[P - k] = cmake(Er + Oi, Ei - Or);
+                    // packed arithmetic: E = a + conj(b), D = a - conj(b), O = conj(W) D;
+                    // conj(2 Z[k]) = conj(E + i O), conj(2 Z[P-k]) = E - i O
+                    const cpx E = cadd_conj(a, bq);
+                    const cpx D = csub_conj(a, bq);
+                    const cpx O = cmul(D, cmake(W.re, -W.im));
+                    const cpx iO = cmake(-O.im, O.re);
+                    const cpx S = cadd(E, iO);
+                    zf[k] = cmake(S.re, -S.im);
+                    if (k != 0) zf[P - k] = csub(E, iO);
                 }
                 if (lane < FPW) {
                     const int fl = warp * FPW + lane;
