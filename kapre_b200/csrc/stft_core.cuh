@@ -727,7 +727,15 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
             for (int i = tid; i < p.n_bd; i += kb_nt) cm_s[i] = p.bd[i];
             for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.bg[i];
         } else if (fbmode) {
-            for (int i = tid; i < p.n_chunks; i += kb_nt) { cw_s[i] = p.cw[i]; cm_s[i] = p.cm[i]; }
+            // chunk descriptors as byte offsets (first bin -> its magnitudes inside a warp's region, band -> its slot in an
+            // out_s row): the loop's dependent load -> address -> load chain is one add long
+            for (int i = tid; i < p.n_chunks; i += kb_nt) {
+                cw_s[i] = p.cw[i];
+                kb_i2 d = p.cm[i];
+                d.x *= FPW * 4;
+                d.y = d.y >= 0 ? d.y * 4 : -1;
+                cm_s[i] = d;
+            }
             for (int i = tid; i <= 32; i += kb_nt) cg_s[i] = p.cg[i];
         }
     KB_PHASE_END
@@ -1055,8 +1063,8 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                 const int ce = cg_s[grp + 1];
                 for (int i = cg_s[grp]; i < ce; ++i) {
                     const kb_f4 wv = cw_s[i];                             // 16 B, uniform within the group
-                    const kb_i2 mt = cm_s[i];
-                    const float* mp = mw + mt.x * FPW;
+                    const kb_i2 mt = cm_s[i];                             // byte offsets (see the table prologue)
+                    const float* mp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(mw) + mt.x);
                     float m01[2 * FPW], m23[2 * FPW];          // bins (k, k+1) and (k+2, k+3), k even
                     kb_load_vec<2 * FPW>(m01, mp);
                     kb_load_vec<2 * FPW>(m23, mp + 2 * FPW);
@@ -1068,9 +1076,10 @@ __device__ __forceinline__ void kb_stft_cta(const KbStftParams& p, char* smem, i
                         a1[g] += wv.w * m23[FPW + g];
                     }
                     if (mt.y >= 0) {
+                        float* ob = reinterpret_cast<float*>(reinterpret_cast<char*>(ocol) + mt.y);
 #pragma unroll
                         for (int g = 0; g < FPW; ++g) {
-                            ocol[g * L.Mp + mt.y] = a0[g] + a1[g];
+                            ob[g * L.Mp] = a0[g] + a1[g];
                             a0[g] = 0.0f;
                             a1[g] = 0.0f;
                         }
