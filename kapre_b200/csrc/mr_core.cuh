@@ -418,12 +418,13 @@ __device__ __forceinline__ void kb_mr_cta_t(const KbMrParams& q, char* smem, int
             KB_PHASE_BEGIN
                 (void)R;
                 const int warp = tid >> 5, lane = tid & 31;
-                if (lane < FRT) {
-                    const float* mcol = mag_s + lane;
-                    for (int m = warp; m < q.n_bands; m += NW) {
-                        const KbBand bd = q.bands[m];
-                        out_s[lane * L.Mp + m] = kb_band_dot<RS>(q.fbw + bd.off, mcol + bd.lo * RS, (bd.hi - bd.lo) >> 2);
-                    }
+                // a tile narrower than a warp (FRT 16 / 8): 32 / FRT bands per trip, so that no lane idles
+                constexpr int FW = FRT > 0 ? FRT : 32, BPT = 32 / FW;
+                const int f = lane & (FW - 1), sub = lane / FW;
+                const float* mcol = mag_s + f;
+                for (int m = warp * BPT + sub; m < q.n_bands; m += NW * BPT) {
+                    const KbBand bd = q.bands[m];
+                    out_s[f * L.Mp + m] = kb_band_dot<RS>(q.fbw + bd.off, mcol + bd.lo * RS, (bd.hi - bd.lo) >> 2);
                 }
             KB_PHASE_END
             KB_SYNC_CTA;
