@@ -13,9 +13,11 @@
 //   twiddles from one shared table exp(-2 pi i m / P).  The first pass writes with a lane stride of r elements; when r is
 //   even that hand-off buffer is indexed as i + (i >> 4) (one spare element per 16), which spreads the 16 lanes of a
 //   half-warp over all banks; later passes (Ns >= r) are at most 2-way conflicted and stay unpadded.
-// Instruction count per frame is about 1.5x the register kernel's at the neighbouring power of two (4 passes over
-// shared memory instead of 1 transpose), against ~100x for the direct O(N^2) DFT it replaces (kb_dft_cta stays for
-// sizes with a prime factor > 5).
+// Everything a pass needs that involves a division (twiddle step, j mod Ns at the group's first butterfly, ...) is
+// precomputed on the host per pass (KbMrPass, kb_mr_finish).  Throughput is about 2.2x below the register kernel at the
+// neighbouring power of two (3-5 passes over shared memory instead of 1 transpose: ~1090 warp instructions per n_fft 400
+// frame, 340 of them butterflies), against ~100x for the direct O(N^2) DFT it replaces (kb_dft_cta stays for sizes
+// with a prime factor > 5).
 #pragma once
 #include "aux_core.cuh"
 #include "stft_mc_core.cuh"   // kb_magic / kb_fdiv

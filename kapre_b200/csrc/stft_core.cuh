@@ -19,9 +19,12 @@
 // z[n] = x[2n] + i x[2n+1]; Q lanes of a warp cooperate on one frame (32/Q frames per warp):
 //   pass 1  lane q: 32-point DFT over j of z[q + Q j]        (registers)
 //           twiddle exp(-2 pi i q k1 / P), transpose through the warp's shared buffer
-//   pass 2  lane q: Q-point DFTs over the columns k1 = q + Q i (registers)
-//           Z[k1 + 32 k2] written back in natural order
+//   pass 2  lane q: Q-point DFTs over its columns (registers)
 //   pair    X[k], X[P-k] from Z[k], Z[P-k] and exp(-2 pi i k / N)  -> output epilogue
+//           paired-column form (n_fft <= 1024, most modes): the lane's columns are k1 = r and 32 - r, so both members of
+//             every pair sit in its own registers (kb_col_gather_paired / kb_col_dftq_pair)
+//           natural-order form (n_fft 2048, complex output at n_fft 512 / 256): columns k1 = q + Q i, Z written back
+//             in natural order and re-read (kb_col_gather / kb_col_dftq_store + phase 4)
 // Filterbank epilogue: magnitudes of the tile stay in shared memory ([bin][frame]); one lane
 // per frame column accumulates a band with warp-uniform weights (vector loads from smem).
 #pragma once
