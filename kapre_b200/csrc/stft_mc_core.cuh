@@ -117,6 +117,24 @@ __device__ __forceinline__ void kb_mc_issue_loads(const KbStftParams& p, float* 
     const float* src = p.x + (long long)b * p.x_sb + (long long)c * p.x_sc + (long long)(s_first + i0) * p.x_sl;
     const long long sstep = (long long)G * p.x_sl;
     float* dst = smp + c * spanp;
+    if (v0 == 0 && v1 >= span) {
+        // whole tile inside the signal (all but the first / last tiles of an item): no per-sample bounds test, the shared
+        // address is stepped as a 32-bit offset -- 4 instructions per sample instead of 13 (ncu on cfg3: the loader was
+        // 29 % of the kernel's instructions)
+#if defined(KB_HOST_EMU)
+        for (int i = i0; i < span; i += G) { dst[i] = *src; src += sstep; }
+#else
+        unsigned d = kb_smem_u32(dst + i0);
+        const unsigned dstep = (unsigned)G * 4u;
+#pragma unroll 8
+        for (int i = i0; i < span; i += G) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+            d += dstep;
+            src += sstep;
+        }
+#endif
+        return;
+    }
 #pragma unroll 4
     for (int i = i0; i < span; i += G) {
         if ((unsigned)(i - v0) < vr) kb_cp_async4(dst + i, src, true);

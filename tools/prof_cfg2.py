@@ -24,6 +24,10 @@ elif mode == 'music':      # n_fft 2048 log-mel: the 16-warp CTA variant
     B, L = 64, 441000
     x = torch.rand((B, L, 1), device='cuda') * 2 - 1
     layer = K.get_melspectrogram_layer(n_fft=2048, hop_length=512, sample_rate=44100, n_mels=128, return_decibel=True)
+elif mode == 'cfg3':      # BASELINE configs[2]: 6-channel channels_last magnitude dB, n_fft 2048 / hop 1024
+    x = torch.rand((1024, 44100, 6), device='cuda') * 2 - 1
+    layer = K.get_stft_magnitude_layer(n_fft=2048, hop_length=1024, return_decibel=True, input_data_format='channels_last',
+                                       output_data_format='channels_last')
 elif mode == 'istft':
     stft, layer = K.get_perfectly_reconstructing_stft_istft(1024, 256, 'channels_last', 'channels_last')
     x = stft(x[:128, :16000])
