@@ -255,3 +255,19 @@ def test_header_is_plain_c_and_c_client_links(tmp_path):
         pytest.skip('gcc not available')
     exe = _build_c_client(str(tmp_path / 'abi_example'))
     assert os.path.exists(exe)
+
+
+def test_host_copy_threads_and_views():
+    """composed._host_copy (the pageable -> page-locked staging copy of Sequential.predict): single memcpy below the
+    threshold, slices over the copy threads above it, odd sizes, and a destination that is a view of a larger buffer."""
+    import numpy as np
+    import torch
+    from kapre_b200.composed import _host_copy
+    rng = np.random.default_rng(0)
+    for shape, min_bytes in (((3, 1001, 1), 1 << 20), ((5, 40001, 2), 1 << 12), ((1, 7), 4), ((4, 250000), 1 << 18)):
+        x = torch.from_numpy(rng.normal(size=shape).astype(np.float32))
+        raw = torch.full((x.numel() * 4 + 64,), 0x7f, dtype=torch.uint8)
+        dst = raw[: x.numel() * 4].view(torch.float32).view(shape)
+        _host_copy(dst, x, min_bytes)
+        assert torch.equal(dst, x)
+        assert bool((raw[x.numel() * 4:] == 0x7f).all())      # nothing written past the view
